@@ -1,0 +1,138 @@
+/* jimm_b200 -- C ABI of the B200-native ViT / CLIP / SigLIP inference forward path.
+ *
+ * The reference (pythoncrazy/jimm) has no FFI boundary: its boundary is the Python class surface
+ * (src/jimm/models/{vit,clip,siglip}.py, src/jimm/common/{vit,transformer}.py).  This header is the C-ABI
+ * underneath the drop-in Python mirror in jimm_b200/ (ctypes binding: jimm_b200/_lib.py; the stub a reference
+ * maintainer would add is shown in INTEGRATION.md).  Each entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - one opaque jimm_model_t per GPU; a handle is not thread-safe, distinct handles are;
+ *   - every call returns 0 on success or a negative jimm_status; the message is in jimm_last_error() (thread-local);
+ *   - "device" pointers are CUDA device pointers on the model's GPU; "host" pointers are CPU memory (pinned memory
+ *     makes the copies asynchronous);
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*; NULL = default stream) and the call
+ *     returns without synchronising, like JAX's asynchronous dispatch (examples/vit_inference.py:54);
+ *   - images are NHWC (tests/test_vit.py:46), token ids int32 [B,T];
+ *   - no C++ exceptions cross this boundary.
+ */
+#ifndef JIMM_B200_H_
+#define JIMM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define JIMM_API __attribute__((visibility("default")))
+#else
+#define JIMM_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jimm_model jimm_model_t;
+
+enum jimm_status { JIMM_OK = 0, JIMM_EINVAL = -1, JIMM_ECUDA = -2, JIMM_EDRIVER = -3, JIMM_ESTATE = -4, JIMM_ENOMEM = -5 };
+enum jimm_dtype { JIMM_F32 = 0, JIMM_F16 = 1, JIMM_BF16 = 2, JIMM_I32 = 3 };
+enum jimm_kind { JIMM_VIT = 0, JIMM_CLIP = 1, JIMM_SIGLIP = 2, JIMM_TOWER = 3 /* bare VisionTransformerBase */ };
+enum jimm_pool { JIMM_POOL_CLS = 0, JIMM_POOL_MAP = 1 };
+enum jimm_act { JIMM_GELU_TANH = 0, JIMM_QUICK_GELU = 1 };
+enum jimm_text_pool { JIMM_TPOOL_EOT_ARGMAX = 0, JIMM_TPOOL_LAST = 1 };
+
+/* Mirrors the constructor kwargs of VisionTransformer (models/vit.py:23-40), VisionTransformerBase
+ * (common/vit.py:107-126), CLIP (models/clip.py:16-31) and SigLIP (models/siglip.py:16-31). */
+typedef struct jimm_config {
+  int kind;                               /* jimm_kind */
+  /* vision tower */
+  int img_size, patch, in_ch, v_width, v_layers, v_heads, v_mlp;
+  int pooling;                            /* jimm_pool */
+  int pre_norm, patch_bias, v_act;        /* use_pre_norm, use_patch_bias, use_quick_gelu */
+  float v_eps_outer;                      /* ln_pre / ln_post / MAP layernorm: 1e-12 ViT | 1e-5 CLIP | 1e-6 SigLIP */
+  float v_eps_block;                      /* encoder-block LayerNorm eps: 1e-6 (common/transformer.py:142; never overridden) */
+  int num_classes;                        /* ViT classifier width; 0 = no classifier (do_classification=False) */
+  /* text tower (CLIP / SigLIP) */
+  int ctx_len, vocab, t_width, t_heads, t_layers, t_mlp;
+  int t_act, t_causal, t_pool, t_head_bias;
+  float t_eps_outer, t_eps_block;
+  /* numerics */
+  int compute_dtype;                      /* jimm_dtype of the tensor-core operands: F32 (tf32 MMA) | F16 | BF16;
+                                             accumulation, residual stream, LN statistics, softmax, logits are fp32 */
+} jimm_config_t;
+
+JIMM_API const char* jimm_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+JIMM_API int jimm_abi_version(void);
+
+/* -- lifecycle: replaces Module.__init__ + from_pretrained's parameter hand-off (models/vit.py:171-257) ----------- */
+JIMM_API int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out);
+/* Hand one parameter over in the reference's flax layout, keyed by the reference's flat-state path joined with '.'
+ * (e.g. "encoder.transformer.blocks.layers.0.attn.query.kernel", shape (D,H,d)).
+ * `host` is read during the call.  dtype: JIMM_F32 | JIMM_F16 | JIMM_BF16. */
+JIMM_API int jimm_model_set_param(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype);
+/* Pack weights (fused [3D,D] QKV, K-major operands, dtype cast), build TMA descriptors, size the workspace for
+ * `max_batch` samples per call.  Fails (JIMM_ESTATE) naming the first missing / unexpected / mis-shaped parameter --
+ * the analogue of the reference's strict visit checks (models/vit.py:229-232,259-268). */
+JIMM_API int jimm_model_finalize(jimm_model_t* m, int max_batch);
+JIMM_API int jimm_model_destroy(jimm_model_t* m);
+/* Introspection used by the Python mirror. */
+JIMM_API int jimm_model_output_dim(const jimm_model_t* m, int* vision_out, int* text_out);
+JIMM_API int jimm_model_max_batch(const jimm_model_t* m);
+
+/* -- forward: device-resident inputs/outputs ---------------------------------------------------------------------- */
+/* VisionTransformer.__call__ (models/vit.py:91-103) / VisionTransformerBase.__call__ (common/vit.py:216-248).
+ * img: device NHWC [B,img,img,in_ch] of in_dtype; out: device fp32 [B, num_classes | v_width]. */
+JIMM_API int jimm_vit_forward(jimm_model_t* m, const void* img, int in_dtype, int B, float* out, void* stream);
+/* CLIP.encode_image (models/clip.py:135-146) / SigLIP.encode_image (models/siglip.py:123-133); out fp32 [B,E]. */
+JIMM_API int jimm_encode_image(jimm_model_t* m, const void* img, int in_dtype, int B, float* out, void* stream);
+/* CLIP.encode_text (models/clip.py:148-167) / SigLIP.encode_text (models/siglip.py:135-153); ids device int32 [B,T]. */
+JIMM_API int jimm_encode_text(jimm_model_t* m, const int32_t* ids, int B, int T, float* out, void* stream);
+/* L2-normalise + exp(logit_scale) * I . T^T (+ logit_bias) (models/clip.py:183-187, models/siglip.py:169-173).
+ * img_e fp32 [Bi,E], txt_e fp32 [Bt,E] (un-normalised encoder outputs), logits fp32 [Bi,Bt] row stride Bt. */
+JIMM_API int jimm_contrastive_logits(jimm_model_t* m, const float* img_e, int Bi, const float* txt_e, int Bt, float* logits, void* stream);
+/* CLIP.__call__ / SigLIP.__call__ (models/clip.py:169-188, models/siglip.py:155-174) on one GPU. */
+JIMM_API int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* logits,
+                      void* stream);
+
+/* -- forward: HOST buffers (the reference-facing call: host->device copy, forward, device->host copy, all enqueued on
+ *    `stream`; the caller synchronises the stream before reading `out`).  examples/vit_inference.py:52-58. ----------- */
+JIMM_API int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream);
+JIMM_API int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int Bi, const int32_t* ids_host, int Bt, int T,
+                           float* logits_host, void* stream);
+
+/* -- multi-GPU contrastive head: one process per GPU, embeddings exchanged over NVLink peer memory ------------------- */
+/* Allocate this rank's symmetric gather buffer ([world*max_rows, 2E] fp32 + flags) and export its IPC handle
+ * (64 bytes).  The handles of all ranks are exchanged by the caller (torch.distributed / any out-of-band channel). */
+JIMM_API int jimm_comm_init(jimm_model_t* m, int rank, int world, int max_rows_per_rank, unsigned char* handle_out /*[64]*/);
+JIMM_API int jimm_comm_connect(jimm_model_t* m, const unsigned char* handles /*[world*64]*/);
+/* Fused: L2-normalise the local [B_local,E] image/text embeddings, store them straight into every peer's gather buffer
+ * over NVLink (st.global on mapped peer pointers), device-side flag barrier, then the local rank's logits row block
+ * logits_local fp32 [B_local, world*B_local] = exp(scale) * I_local . T_all^T (+ bias).  No host synchronisation. */
+JIMM_API int jimm_comm_contrastive_logits(jimm_model_t* m, const float* img_e, const float* txt_e, int B_local, float* logits_local,
+                                 void* stream);
+/* Device pointer to this rank's gathered, normalised [world*B_local, 2E] buffer (valid after the call above). */
+JIMM_API int jimm_comm_gathered(jimm_model_t* m, float** gathered, int* row_stride);
+
+/* -- per-kernel entry points (device pointers; used by tests/ and the ncu harness so every kernel is individually
+ *    parity- and profile-testable) ------------------------------------------------------------------- */
+/* C[M,N] = epi(A[M,K] . B[N,K]^T): impl 0 = tcgen05/TMA kernel, 1 = SIMT cross-check.
+ * act: 0 none | 1 gelu_tanh | 2 quick_gelu; epi_mode 0 staged | 1 direct; rows_in>0 remaps output rows. */
+JIMM_API int jimm_k_gemm(int impl, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
+                const float* rowadd, const float* residual, int ldr, void* out, int out_type, int ldo, int rows_in, int rows_out,
+                int row_off, int epi_mode, void* stream);
+JIMM_API int jimm_k_layernorm(const float* x, int ldx, int group, int row_off, const int32_t* row_index, const float* scale, const float* bias,
+                     float eps, void* out, int out_type, int ldy, int rows, int D, void* stream);
+JIMM_API int jimm_k_attention(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, void* stream);
+JIMM_API int jimm_k_map_attention(const float* q, const void* kv, int io_type, void* out, int out_type, int B, int S, int H, void* stream);
+JIMM_API int jimm_k_patchify(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, void* stream);
+JIMM_API int jimm_k_embed(const int32_t* ids, const float* table, const float* pos, float* x, int B, int T, int D, int vocab, void* stream);
+JIMM_API int jimm_k_l2_normalize(const float* x, float* out, int ldo, int B, int E, void* stream);
+JIMM_API int jimm_k_logits(const float* img, const float* txt, const float* logit_scale, const float* logit_bias, float* logits, int Bi, int Bt,
+                  int E, int ldl, void* stream);
+/* Count of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+JIMM_API long long jimm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JIMM_B200_H_ */

@@ -1,0 +1,194 @@
+"""Native model handle: drives jimm_model_create -> set_param x N -> finalize, and the forward entry points, for the
+Python mirror classes.  PyTorch is used only for device memory, streams and torch.distributed plumbing."""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_TO_CODE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_tensor(x, what: str) -> torch.Tensor:
+    if isinstance(x, torch.Tensor):
+        return x
+    if isinstance(x, np.ndarray):
+        return torch.from_numpy(np.ascontiguousarray(x))
+    if hasattr(x, "__dlpack__"):
+        return torch.from_dlpack(x)
+    return torch.as_tensor(np.asarray(x))
+
+
+class NativeModel:
+    """One opaque jimm_model_t on one GPU."""
+
+    def __init__(self, cfg: _lib.Config, params: Dict[str, torch.Tensor], max_batch: int, device: Optional[int] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.JimmError("jimm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.cfg = cfg
+        self.handle = C.c_void_p()
+        _lib.check(self.lib.jimm_model_create(C.byref(cfg), self.device_index, C.byref(self.handle)))
+        try:
+            for name, t in params.items():
+                t = t.detach()
+                if t.dtype not in _TORCH_TO_CODE:
+                    t = t.to(torch.float32)
+                t = t.contiguous().cpu()
+                shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
+                _lib.check(self.lib.jimm_model_set_param(self.handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.ndim,
+                                                          _TORCH_TO_CODE[t.dtype]))
+            _lib.check(self.lib.jimm_model_finalize(self.handle, int(max_batch)))
+        except Exception:
+            self.lib.jimm_model_destroy(self.handle)
+            self.handle = None
+            raise
+        self.max_batch = int(max_batch)
+        vo, to = C.c_int(), C.c_int()
+        _lib.check(self.lib.jimm_model_output_dim(self.handle, C.byref(vo), C.byref(to)))
+        self.vision_out, self.text_out = vo.value, to.value
+        self._comm = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.jimm_model_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- input normalisation ----
+    def _prep_images(self, x) -> torch.Tensor:
+        x = _as_tensor(x, "image")
+        if x.ndim != 4:
+            raise ValueError(f"expected images of shape [batch, height, width, channels], got {tuple(x.shape)}")
+        c = self.cfg
+        if x.shape[1] != c.img_size or x.shape[2] != c.img_size or x.shape[3] != c.in_ch:
+            raise ValueError(f"expected NHWC images [B,{c.img_size},{c.img_size},{c.in_ch}], got {tuple(x.shape)}")
+        if x.dtype not in _TORCH_TO_CODE:
+            x = x.to(torch.float32)
+        return x.contiguous()
+
+    def _prep_ids(self, t) -> torch.Tensor:
+        t = _as_tensor(t, "text")
+        if t.ndim != 2:
+            raise ValueError(f"expected token ids of shape [batch, context_length], got {tuple(t.shape)}")
+        return t.to(torch.int32).contiguous()
+
+    # ---- forward ----
+    def vision(self, x, encode: bool = False) -> torch.Tensor:
+        """VisionTransformer.__call__ / encode_image.  CUDA input -> async CUDA output; host input -> host output."""
+        x = self._prep_images(x)
+        B = x.shape[0]
+        fn_dev = self.lib.jimm_encode_image if encode else self.lib.jimm_vit_forward
+        if x.is_cuda:
+            with torch.cuda.device(self.device):
+                out = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
+                _lib.check(fn_dev(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(out.data_ptr()),
+                                  C.c_void_p(_stream_ptr(self.device))))
+            return out
+        # host path: H2D + forward + D2H enqueued by the library on the current stream
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, self.vision_out), dtype=torch.float32, pin_memory=True)
+            if encode:
+                xd = x.to(self.device, non_blocking=True)
+                od = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
+                _lib.check(fn_dev(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(od.data_ptr()),
+                                  C.c_void_p(_stream_ptr(self.device))))
+                out.copy_(od, non_blocking=True)
+            else:
+                _lib.check(self.lib.jimm_vit_forward_host(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B,
+                                                          C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+            torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def text(self, ids) -> torch.Tensor:
+        ids = self._prep_ids(ids)
+        host = not ids.is_cuda
+        B, T = ids.shape
+        with torch.cuda.device(self.device):
+            idd = ids.to(self.device, non_blocking=True)
+            out = torch.empty((B, self.text_out), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.jimm_encode_text(self.handle, C.c_void_p(idd.data_ptr()), B, T, C.c_void_p(out.data_ptr()),
+                                                 C.c_void_p(_stream_ptr(self.device))))
+            if host:
+                out = out.cpu()
+        return out
+
+    def logits(self, img_e: torch.Tensor, txt_e: torch.Tensor) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            img_e = img_e.to(self.device, torch.float32).contiguous()
+            txt_e = txt_e.to(self.device, torch.float32).contiguous()
+            Bi, Bt = img_e.shape[0], txt_e.shape[0]
+            out = torch.empty((Bi, Bt), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.jimm_contrastive_logits(self.handle, C.c_void_p(img_e.data_ptr()), Bi, C.c_void_p(txt_e.data_ptr()), Bt,
+                                                        C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        return out
+
+    def dual(self, image, text) -> torch.Tensor:
+        """CLIP.__call__ / SigLIP.__call__ on one GPU."""
+        x = self._prep_images(image)
+        ids = self._prep_ids(text)
+        Bi, (Bt, T) = x.shape[0], ids.shape
+        with torch.cuda.device(self.device):
+            if not x.is_cuda and not ids.is_cuda:
+                out = torch.empty((Bi, Bt), dtype=torch.float32, pin_memory=True)
+                _lib.check(self.lib.jimm_dual_forward_host(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], Bi,
+                                                           C.c_void_p(ids.data_ptr()), Bt, T, C.c_void_p(out.data_ptr()),
+                                                           C.c_void_p(_stream_ptr(self.device))))
+                torch.cuda.current_stream(self.device).synchronize()
+                return out
+            xd, idd = x.to(self.device, non_blocking=True), ids.to(self.device, non_blocking=True)
+            out = torch.empty((Bi, Bt), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.jimm_dual_forward(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[xd.dtype], Bi,
+                                                  C.c_void_p(idd.data_ptr()), Bt, T, C.c_void_p(out.data_ptr()),
+                                                  C.c_void_p(_stream_ptr(self.device))))
+        return out
+
+    # ---- multi-GPU contrastive head (one process per GPU; torch.distributed is the control plane) ----
+    def comm_setup(self, max_rows_per_rank: int, group=None):
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle = C.create_string_buffer(64)
+        _lib.check(self.lib.jimm_comm_init(self.handle, rank, world, int(max_rows_per_rank), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        _lib.check(self.lib.jimm_comm_connect(self.handle, b"".join(handles)))
+        dist.barrier(group)
+        self._comm = (rank, world, int(max_rows_per_rank))
+
+    def comm_logits(self, img_e: torch.Tensor, txt_e: torch.Tensor) -> torch.Tensor:
+        """Fused normalise + NVLink peer scatter + local logits row block [B_local, world*B_local]."""
+        if self._comm is None:
+            raise _lib.JimmError("comm_setup() has not been called")
+        rank, world, _ = self._comm
+        with torch.cuda.device(self.device):
+            img_e = img_e.to(self.device, torch.float32).contiguous()
+            txt_e = txt_e.to(self.device, torch.float32).contiguous()
+            B = img_e.shape[0]
+            if txt_e.shape[0] != B:
+                raise ValueError("multi-GPU contrastive head needs equal image/text batch per rank")
+            out = torch.empty((B, world * B), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.jimm_comm_contrastive_logits(self.handle, C.c_void_p(img_e.data_ptr()), C.c_void_p(txt_e.data_ptr()), B,
+                                                             C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        return out
+
+
+def default_max_batch() -> int:
+    return int(os.environ.get("JIMM_MAX_BATCH", "256"))

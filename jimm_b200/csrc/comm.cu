@@ -1,0 +1,168 @@
+// Fused L2-normalise -> all-gather over NVLink peer memory -> contrastive logits, in ONE kernel.
+//
+// Reference op: under batch sharding the only place data from different shards meets is
+//   logits = exp(logit_scale) * image_features @ text_features.T (+ logit_bias)      models/clip.py:183-187, models/siglip.py:169-173
+// which XLA's GSPMD resolves with an all-gather of the features.  Here every rank
+//   phase 1  L2-normalises its [B_local, E] image and text rows and stores them straight into EVERY peer's gather buffer
+//            (st.global on CUDA-IPC-mapped peer pointers -> NVLink 5 / NVSwitch), row (rank*B_local + r), cols [0,E) | [E,2E);
+//   phase 2  fences (system scope); the last CTA to finish publishes flag[rank] = epoch into every peer (st.release.sys);
+//   phase 3  every CTA spins (ld.acquire.sys) on its LOCAL flags until all ranks have published this epoch;
+//   phase 4  computes its own logits row block [B_local, world*B_local] from local memory only (fp32 FMA tiles).
+// The grid is persistent (<= #SMs CTAs, 1 CTA/SM) so the phase-3 spin cannot starve phase 1/2 of a co-resident CTA.
+// Two parity buffers make back-to-back calls safe without a host barrier: a peer can only be one epoch ahead.
+#include <string.h>
+
+#include "comm.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "logits_tile.cuh"
+
+namespace jimm {
+
+static constexpr size_t kFlagsBytes = 4096;
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct CommPtrs {
+  float* buf[kMaxWorld];          // this epoch's parity buffer on each rank
+  unsigned int* flags[kMaxWorld]; // flags array on each rank
+};
+
+__global__ void __launch_bounds__(256, 1)
+comm_logits_kernel(CommPtrs ptrs, const float* __restrict__ img_e, const float* __restrict__ txt_e, int B_local, int E, int rank,
+                   int world, unsigned int epoch, unsigned int* counter, const float* __restrict__ logit_scale,
+                   const float* __restrict__ logit_bias, float* __restrict__ logits_local) {
+  __shared__ float As[16][65], Bs[16][65];
+  __shared__ int s_last;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t ld = static_cast<size_t>(2) * E;
+
+  // ---- phase 1: normalise + scatter to all peers ----
+  const int total_rows = 2 * B_local;  // image rows then text rows
+  for (int r = blockIdx.x * 8 + warp; r < total_rows; r += gridDim.x * 8) {
+    const bool is_txt = r >= B_local;
+    const int row = is_txt ? r - B_local : r;
+    const float* src = (is_txt ? txt_e : img_e) + static_cast<size_t>(row) * E;
+    float ss = 0.f;
+    for (int i = lane; i < E; i += 32) { const float v = src[i]; ss += v * v; }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    const size_t dst_off = (static_cast<size_t>(rank) * B_local + row) * ld + (is_txt ? E : 0);
+    for (int i = lane; i < E; i += 32) {
+      const float v = src[i] / nrm;
+      for (int p = 0; p < world; ++p) ptrs.buf[p][dst_off + i] = v;
+    }
+  }
+  // ---- phase 2: publish ----
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(counter, 1u);
+    s_last = (ticket == epoch * gridDim.x - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(ptrs.flags[threadIdx.x] + rank, epoch);
+  }
+  // ---- phase 3: wait for every rank's rows of this epoch ----
+  if (threadIdx.x < world) {
+    const unsigned int* f = ptrs.flags[rank] + threadIdx.x;
+    while (static_cast<int>(ld_acquire_sys(f) - epoch) < 0) { __nanosleep(64); }
+  }
+  __syncthreads();
+  // ---- phase 4: local logits row block ----
+  const float sc = expf(*logit_scale);
+  const float bs = logit_bias ? *logit_bias : 0.f;
+  const int Bt = world * B_local;
+  const float* gathered = ptrs.buf[rank];
+  const float* A = gathered + static_cast<size_t>(rank) * B_local * ld;  // my normalised image rows
+  const float* Bm = gathered + E;                                         // all normalised text rows
+  const int ti = (B_local + 63) / 64, tj = (Bt + 63) / 64;
+  for (int t = blockIdx.x; t < ti * tj; t += gridDim.x) {
+    const int i0 = (t / tj) * 64, j0 = (t % tj) * 64;
+    logits_tile<true>(A, ld, Bm, ld, logits_local, Bt, B_local, Bt, E, i0, j0, sc, bs, As, Bs);
+  }
+}
+
+int comm_init(CommState* c, int rank, int world, int max_rows, int E, unsigned char* handle_out) {
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || max_rows <= 0 || E <= 0 || !handle_out) {
+    set_last_error("comm_init: bad arguments (rank %d world %d rows %d E %d)", rank, world, max_rows, E);
+    return -1;
+  }
+  if (c->ready) { set_last_error("comm already initialised"); return -4; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  c->rank = rank; c->world = world; c->max_rows = max_rows; c->E = E;
+  c->buf_floats = static_cast<size_t>(world) * max_rows * 2 * E;
+  const size_t bytes = 2 * c->buf_floats * sizeof(float) + kFlagsBytes;
+  JIMM_CUDA_CHECK(cudaMalloc(&c->base, bytes));
+  JIMM_CUDA_CHECK(cudaMemset(c->base, 0, bytes));
+  JIMM_CUDA_CHECK(cudaMalloc(&c->counter, sizeof(unsigned int)));
+  JIMM_CUDA_CHECK(cudaMemset(c->counter, 0, sizeof(unsigned int)));
+  JIMM_CUDA_CHECK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  JIMM_CUDA_CHECK(cudaIpcGetMemHandle(&h, c->base));
+  memcpy(handle_out, &h, sizeof(h));
+  for (int i = 0; i < kMaxWorld; ++i) c->peer_base[i] = nullptr;
+  c->peer_base[rank] = c->base;
+  c->local_buf = static_cast<float*>(c->base);
+  c->grid = device_sm_count();
+  if (c->grid > 64) c->grid = 64;  // tiny op: 64 CTAs cover the row scatter and the logits tiles
+  c->epoch = 0;
+  c->ready = true;
+  c->connected = (world == 1);
+  return 0;
+}
+
+int comm_connect(CommState* c, const unsigned char* handles) {
+  if (!c->ready) { set_last_error("comm_connect before comm_init"); return -4; }
+  if (!handles) { set_last_error("comm_connect: null handles"); return -1; }
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + static_cast<size_t>(r) * 64, 64);
+    void* p = nullptr;
+    JIMM_CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[r] = p;
+  }
+  c->connected = true;
+  return 0;
+}
+
+int comm_contrastive_logits(CommState* c, const float* img_e, const float* txt_e, int B_local, const float* logit_scale,
+                            const float* logit_bias, float* logits_local, cudaStream_t stream) {
+  if (!c->ready || !c->connected) { set_last_error("comm not initialised / connected"); return -4; }
+  if (B_local <= 0 || B_local > c->max_rows) { set_last_error("comm: B_local %d outside (0, %d]", B_local, c->max_rows); return -1; }
+  c->epoch += 1;
+  const int parity = static_cast<int>(c->epoch & 1);
+  CommPtrs ptrs;
+  for (int r = 0; r < kMaxWorld; ++r) { ptrs.buf[r] = nullptr; ptrs.flags[r] = nullptr; }
+  for (int r = 0; r < c->world; ++r) {
+    uint8_t* b = static_cast<uint8_t*>(c->peer_base[r]);
+    ptrs.buf[r] = reinterpret_cast<float*>(b) + static_cast<size_t>(parity) * c->buf_floats;
+    ptrs.flags[r] = reinterpret_cast<unsigned int*>(b + 2 * c->buf_floats * sizeof(float));
+  }
+  c->local_buf = ptrs.buf[c->rank];
+  comm_logits_kernel<<<c->grid, 256, 0, stream>>>(ptrs, img_e, txt_e, B_local, c->E, c->rank, c->world,
+                                                  static_cast<unsigned int>(c->epoch), c->counter, logit_scale, logit_bias, logits_local);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
+void comm_destroy(CommState* c) {
+  if (!c->ready) return;
+  for (int r = 0; r < c->world; ++r)
+    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->base) cudaFree(c->base);
+  if (c->counter) cudaFree(c->counter);
+  c->ready = false;
+}
+
+}  // namespace jimm

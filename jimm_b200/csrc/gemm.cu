@@ -1,0 +1,464 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a with fused epilogues.
+//
+//   C[M,N] = epi( A[M,K] . B[N,K]^T ),  A/B K-major fp16 | bf16 | fp32(tf32), fp32 accumulate in TMEM.
+//
+// CTA = 256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule.
+//   warp 0   : TMA producer (one lane): 4-stage smem ring of {A 128x128B, B 256x128B} tiles, SWIZZLE_128B
+//   warp 1   : MMA issuer  (one lane): tcgen05.mma.cta_group::1 128x256xUMMA_K, accumulators double-buffered
+//              in TMEM (2 x 256 columns), tcgen05.commit releases smem stages / publishes accumulators
+//   warp 2   : TMEM allocator (512 columns)
+//   warps 4-7: epilogue: tcgen05.ld 32x32b.x32 -> bias / GELU / QuickGELU / pos-emb / fp32 residual -> global
+// Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
+//
+// Reference ops served: a1 patch-embed conv-as-GEMM (common/vit.py:153-165,228-236),
+// a4 fused q/k/v projections (common/transformer.py:67-79), a6 out-proj + residual (:130),
+// a7 MLP (:90-114,131), a9 MAP-head linears (common/vit.py:42-85), a10 classifier / projections
+// (models/vit.py:81-89, models/clip.py:82-90,166, models/siglip.py:111-119).
+#include "gemm.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace jimm {
+
+static constexpr int BM = 128;
+static constexpr int BN = 256;
+static constexpr int STAGES = 4;
+static constexpr int A_STAGE_BYTES = BM * 128;
+static constexpr int B_STAGE_BYTES = BN * 128;
+static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+static constexpr int EPI_PITCH = 36;  // floats; conflict-free for 128-bit accesses
+static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_PITCH * 4;
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 256 + 1024;
+static constexpr int NUM_THREADS = 256;
+static constexpr uint32_t TMEM_COLS = 512;
+
+struct EpiDev {
+  const float* bias;
+  const float* rowadd;
+  const float* residual;
+  void* out;
+  int act, ldr, out_type, ldo, rows_in, rows_out, row_off, mode;
+  int M, N;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_GELU_TANH) return gelu_tanh(v);
+  if (act == ACT_QUICK_GELU) return quick_gelu(v);
+  return v;
+}
+
+__device__ __forceinline__ void remap_row(const EpiDev& e, int row, int& out_row, int& add_row) {
+  if (e.rows_in > 0) {
+    int b = row / e.rows_in, p = row - b * e.rows_in;
+    out_row = b * e.rows_out + p + e.row_off;
+    add_row = p + e.row_off;
+  } else {
+    out_row = row;
+    add_row = row;
+  }
+}
+
+// Store 4 consecutive columns (col % 4 == 0, col + 3 < N guaranteed by caller).
+__device__ __forceinline__ void store4(const EpiDev& e, int out_row, int col, float4 v) {
+  size_t off = static_cast<size_t>(out_row) * e.ldo + col;
+  if (e.out_type == DT_F32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(e.out) + off) = v;
+  } else {
+    uint2 p;
+    p.x = pack2(v.x, v.y, e.out_type);
+    p.y = pack2(v.z, v.w, e.out_type);
+    *reinterpret_cast<uint2*>(static_cast<uint16_t*>(e.out) + off) = p;
+  }
+}
+__device__ __forceinline__ void store1(const EpiDev& e, int out_row, int col, float v) {
+  size_t off = static_cast<size_t>(out_row) * e.ldo + col;
+  if (e.out_type == DT_F32) static_cast<float*>(e.out)[off] = v;
+  else if (e.out_type == DT_F16) static_cast<__half*>(e.out)[off] = __float2half_rn(v);
+  else static_cast<__nv_bfloat16*>(e.out)[off] = __float2bfloat16_rn(v);
+}
+
+template <typename T>
+struct Traits;
+template <>
+struct Traits<__half> {
+  static constexpr int KIND = 0, FMT = 0;
+};
+template <>
+struct Traits<__nv_bfloat16> {
+  static constexpr int KIND = 0, FMT = 1;
+};
+template <>
+struct Traits<float> {
+  static constexpr int KIND = 1, FMT = 2;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiDev epi, int K) {
+  constexpr int BK = 128 / sizeof(T);  // one 128-byte swizzle atom along K per stage
+  constexpr int UK = 32 / sizeof(T);   // UMMA K (16 for 16-bit, 8 for tf32)
+  constexpr uint32_t IDESC = make_idesc(Traits<T>::FMT, BM, BN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES; // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;// [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int M = epi.M, N = epi.N;
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t adesc = make_umma_desc_sw128(a_addr + k * 32);
+            const uint64_t bdesc = make_umma_desc_sw128(b_addr + k * 32);
+            umma_ss<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          tcgen05_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
+          if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
+    float* st = epi_stage + q * 32 * EPI_PITCH;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row_base = m_blk * BM + q * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (row_base < M) {
+        for (int c = 0; c < BN / 32; ++c) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= N) break;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+          if (epi.mode == 1) {
+            // ---- direct: thread owns one row, 32 consecutive columns ----
+            const int row = row_base + lane;
+            if (row < M) {
+              int out_row, add_row;
+              remap_row(epi, row, out_row, add_row);
+              const bool full = (n0 + 32 <= N);
+              if (full && epi.out_type != DT_F32 && epi.rowadd == nullptr && epi.residual == nullptr) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                  float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
+                  if (epi.bias) { v0 += __ldg(epi.bias + n0 + j); v1 += __ldg(epi.bias + n0 + j + 1); }
+                  v0 = apply_act(v0, epi.act);
+                  v1 = apply_act(v1, epi.act);
+                  pk[j >> 1] = pack2(v0, v1, epi.out_type);
+                }
+                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(epi.out) + static_cast<size_t>(out_row) * epi.ldo + n0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const int col = n0 + j;
+                  if (col < N) {
+                    float v = __uint_as_float(r[j]);
+                    if (epi.bias) v += __ldg(epi.bias + col);
+                    v = apply_act(v, epi.act);
+                    if (epi.rowadd) v += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + col);
+                    if (epi.residual) v += epi.residual[static_cast<size_t>(out_row) * epi.ldr + col];
+                    store1(epi, out_row, col, v);
+                  }
+                }
+              }
+            }
+          } else {
+            // ---- staged: transpose through smem so every global access is a full 128-byte line ----
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(st + lane * EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            __syncwarp();
+            const int cq = (lane & 7) * 4;
+            const int col = n0 + cq;
+            const bool col_ok = (col + 3 < N);
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (epi.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + (lane >> 3);
+              const int row = row_base + rr;
+              float4 v = *reinterpret_cast<const float4*>(st + rr * EPI_PITCH + cq);
+              if (row < M) {
+                int out_row, add_row;
+                remap_row(epi, row, out_row, add_row);
+                if (col_ok) {
+                  v.x = apply_act(v.x + b4.x, epi.act);
+                  v.y = apply_act(v.y + b4.y, epi.act);
+                  v.z = apply_act(v.z + b4.z, epi.act);
+                  v.w = apply_act(v.w + b4.w, epi.act);
+                  if (epi.rowadd) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(epi.rowadd + static_cast<size_t>(add_row) * N + col));
+                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                  }
+                  if (epi.residual) {
+                    const float4 a = *reinterpret_cast<const float4*>(epi.residual + static_cast<size_t>(out_row) * epi.ldr + col);
+                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                  }
+                  store4(epi, out_row, col, v);
+                } else {
+                  const float vv[4] = {v.x, v.y, v.z, v.w};
+                  for (int j = 0; j < 4; ++j) {
+                    const int cc = col + j;
+                    if (cc < N) {
+                      float x = vv[j];
+                      if (epi.bias) x += __ldg(epi.bias + cc);
+                      x = apply_act(x, epi.act);
+                      if (epi.rowadd) x += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + cc);
+                      if (epi.residual) x += epi.residual[static_cast<size_t>(out_row) * epi.ldr + cc];
+                      store1(epi, out_row, cc, x);
+                    }
+                  }
+                }
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// SIMT reference GEMM (bring-up cross-check / JIMM_GEMM_IMPL=simt bisection only)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gemm_simt_kernel(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int K, EpiDev epi) {
+  __shared__ float As[16][17], Bs[16][17];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    const int ar = blockIdx.y * 16 + ty, ak = k0 + tx;
+    As[ty][tx] = (ar < epi.M && ak < K) ? to_float(A[static_cast<size_t>(ar) * lda + ak]) : 0.f;
+    const int br = blockIdx.x * 16 + ty, bk = k0 + tx;
+    Bs[ty][tx] = (br < epi.N && bk < K) ? to_float(B[static_cast<size_t>(br) * ldb + bk]) : 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc += As[ty][k] * Bs[tx][k];
+    __syncthreads();
+  }
+  if (row < epi.M && col < epi.N) {
+    int out_row, add_row;
+    remap_row(epi, row, out_row, add_row);
+    float v = acc;
+    if (epi.bias) v += epi.bias[col];
+    v = apply_act(v, epi.act);
+    if (epi.rowadd) v += epi.rowadd[static_cast<size_t>(add_row) * epi.N + col];
+    if (epi.residual) v += epi.residual[static_cast<size_t>(out_row) * epi.ldr + col];
+    store1(epi, out_row, col, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) {
+    set_last_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = reinterpret_cast<PFN_encodeTiled>(p);
+  return fn;
+}
+
+// 2-D K-major tensor map: dims {K, rows}, box {128 B worth of K, box_rows}, SWIZZLE_128B, zero OOB fill.
+static int make_map(CUtensorMap* map, int dtype, const void* ptr, int rows, int K, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -3;
+  const size_t es = dtype_size(dtype);
+  CUtensorMapDataType dt = dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * es};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / es), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (strides[0] & 15) != 0) {
+    set_last_error("gemm: operand pointer/stride must be 16-byte aligned (ptr=%p, ld=%d)", ptr, ld);
+    return -1;
+  }
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%d K=%d ld=%d)", static_cast<int>(r), rows, K, ld);
+    return -3;
+  }
+  return 0;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* env = getenv("JIMM_NUM_SMS");
+    if (env && atoi(env) > 0) sms = atoi(env);
+  }
+  return sms;
+}
+
+static int check_epi(const GemmEpilogue& e, int N) {
+  if (e.out == nullptr) { set_last_error("gemm: null output"); return -1; }
+  if (e.ldo % 4 != 0 || N % 4 != 0) { set_last_error("gemm: N (%d) and ldo (%d) must be multiples of 4", N, e.ldo); return -1; }
+  if (e.residual && e.ldr % 4 != 0) { set_last_error("gemm: ldr must be a multiple of 4"); return -1; }
+  if (e.mode == 1 && e.out_type != DT_F32 && e.ldo % 8 != 0) { set_last_error("gemm: direct 16-bit epilogue needs ldo %% 8 == 0"); return -1; }
+  return 0;
+}
+
+int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                   const GemmEpilogue& epi) {
+  if (M <= 0 || N <= 0 || K <= 0) { set_last_error("gemm: bad shape %dx%dx%d", M, N, K); return -1; }
+  if (int rc = check_epi(epi, N)) return rc;
+  if (int rc = make_map(&plan->map_a, dtype, A, M, K, lda, BM)) return rc;
+  if (int rc = make_map(&plan->map_b, dtype, B, N, K, ldb, BN)) return rc;
+  plan->M = M; plan->N = N; plan->K = K; plan->dtype = dtype; plan->epi = epi;
+  return 0;
+}
+
+static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
+  EpiDev d;
+  d.bias = e.bias; d.rowadd = e.rowadd; d.residual = e.residual; d.out = e.out;
+  d.act = e.act; d.ldr = e.ldr; d.out_type = e.out_type; d.ldo = e.ldo;
+  d.rows_in = e.rows_in; d.rows_out = e.rows_out; d.row_off = e.row_off; d.mode = e.mode;
+  d.M = M; d.N = N;
+  return d;
+}
+
+template <typename T>
+static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_tcgen05_kernel<T><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, to_dev(p->epi, M, p->N), p->K);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
+int gemm_plan_run(const GemmPlan* p, int M_override, cudaStream_t stream) {
+  const int M = (M_override > 0 && M_override <= p->M) ? M_override : p->M;
+  switch (p->dtype) {
+    case DT_F16: return launch_tc<__half>(p, M, stream);
+    case DT_BF16: return launch_tc<__nv_bfloat16>(p, M, stream);
+    case DT_F32: return launch_tc<float>(p, M, stream);
+  }
+  set_last_error("gemm: bad dtype %d", p->dtype);
+  return -1;
+}
+
+int gemm_simt_run(int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmEpilogue& epi,
+                  cudaStream_t stream) {
+  if (int rc = check_epi(epi, N)) return rc;
+  dim3 block(16, 16), grid((N + 15) / 16, (M + 15) / 16);
+  EpiDev d = to_dev(epi, M, N);
+  if (dtype == DT_F16) gemm_simt_kernel<__half><<<grid, block, 0, stream>>>(static_cast<const __half*>(A), lda, static_cast<const __half*>(B), ldb, K, d);
+  else if (dtype == DT_BF16) gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda, static_cast<const __nv_bfloat16*>(B), ldb, K, d);
+  else gemm_simt_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(A), lda, static_cast<const float*>(B), ldb, K, d);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace jimm

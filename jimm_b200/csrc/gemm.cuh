@@ -1,0 +1,55 @@
+// Host-side interface of the tcgen05/TMA GEMM (gemm.cu).
+//
+//   C[M,N] = epilogue( A[M,K] . B[N,K]^T )      A, B K-major ("TN"), fp32 accumulate in TMEM
+//
+// This one kernel serves every dense contraction on the jimm forward path
+// (SURVEY.md 8a rows a1,a4,a6,a7,a9,a10): patch-embed, fused QKV, attention
+// out-projection (+residual), MLP FC1 (+GELU/QuickGELU), FC2 (+residual), MAP-head
+// k/v + MLP, classifier / projections.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jimm {
+
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_QUICK_GELU = 2 };
+
+inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+struct GemmEpilogue {
+  const float* bias = nullptr;      // [N] fp32, added per output column
+  int act = ACT_NONE;               // applied after bias
+  const float* rowadd = nullptr;    // fp32 [*, N]; row (r % rows_in + row_off) added (position embeddings)
+  const float* residual = nullptr;  // fp32, indexed like the output (out_row, ldr); may alias out
+  int ldr = 0;
+  void* out = nullptr;
+  int out_type = DT_F32;
+  int ldo = 0;                                   // output row stride (elements)
+  int rows_in = 0, rows_out = 0, row_off = 0;    // out_row = (r / rows_in) * rows_out + r % rows_in + row_off (rows_in == 0: identity)
+  int mode = 0;                                  // 0: smem-staged, coalesced stores; 1: direct row-per-thread stores
+};
+
+struct GemmPlan {
+  CUtensorMap map_a, map_b;
+  int M = 0, N = 0, K = 0;
+  int dtype = DT_F16;  // operand type: DT_F16 / DT_BF16 / DT_F32 (tf32 MMA)
+  GemmEpilogue epi;
+};
+
+// Build TMA descriptors for A [M,K] (row stride lda elements) and B [N,K] (row stride ldb).
+// Returns 0 or a negative status (message in jimm_last_error()).
+int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
+                   const GemmEpilogue& epi);
+// Enqueue on `stream`; M may be overridden (<= planned M) to run on fewer rows of the same buffers.
+int gemm_plan_run(const GemmPlan* plan, int M_override, cudaStream_t stream);
+
+// Simple SIMT reference GEMM (debug / bring-up cross-check on the GPU; never on the product path
+// unless JIMM_GEMM_IMPL=simt is set for bisection).
+int gemm_simt_run(int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const GemmEpilogue& epi,
+                  cudaStream_t stream);
+
+int device_sm_count();
+
+}  // namespace jimm

@@ -1,0 +1,857 @@
+// Model state, weight packing, forward orchestration and the C ABI (include/jimm_b200.h).
+//
+// Host-side structure mirrors the reference's module tree:
+//   Tower (VisionTransformerBase, common/vit.py:104-248)  -> patch GEMM, cls/pos, [ln_pre], L x Block, ln_post, CLS | MAP head
+//   Block (TransformerEncoder, common/transformer.py:22-132)
+//   TextTower (nnx.Embed + Transformer + ln_final + pooling; models/clip.py:148-167, models/siglip.py:135-153)
+//   heads (classifier / visual_projection / text_projection; contrastive logits)
+// All arithmetic is in the kernels of gemm.cu / attention.cu / elementwise.cu / comm.cu; there is no CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/jimm_b200.h"
+#include "comm.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace jimm {
+
+// ------------------------------------------------------------------------------------------
+// error + launch accounting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+static std::atomic<long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+#define JIMM_TRY(expr)          \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != 0) return _rc;   \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// small RAII-free device memory pool (freed in model destroy)
+// ------------------------------------------------------------------------------------------
+struct DevPool {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  int alloc(void** out, size_t n) {
+    if (n == 0) n = 16;
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      set_last_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+      return JIMM_ENOMEM;
+    }
+    ptrs.push_back(p);
+    bytes += n;
+    *out = p;
+    return 0;
+  }
+  void release() {
+    for (void* p : ptrs) cudaFree(p);
+    ptrs.clear();
+    bytes = 0;
+  }
+};
+
+struct HostParam {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool used = false;
+  size_t numel() const { return data.size(); }
+};
+
+struct LinearW {
+  void* w = nullptr;   // [N, K] compute dtype, K-major
+  float* b = nullptr;  // [N] fp32 or null
+  int N = 0, K = 0;
+};
+struct LNW {
+  float* scale = nullptr;
+  float* bias = nullptr;
+};
+struct BlockW {
+  LNW norm1, norm2;
+  LinearW qkv, out, fc1, fc2;
+  GemmPlan p_qkv, p_out, p_fc1, p_fc2;
+};
+
+struct EncoderCfg {  // one Transformer stack
+  int D = 0, H = 0, M = 0, L = 0, act = 0, causal = 0;
+  float eps = 1e-6f;
+};
+
+struct Encoder {
+  EncoderCfg c;
+  std::vector<BlockW> blocks;
+};
+
+struct VisionTower {
+  bool present = false;
+  int img = 0, P = 0, C = 0, D = 0, n = 0, S = 0, pooling = 0, pre_norm = 0, patch_bias = 0;
+  float eps_outer = 1e-5f;
+  Encoder enc;
+  LinearW patch;
+  float* cls = nullptr;
+  float* pos = nullptr;  // [S, D]
+  LNW ln_pre, ln_post;
+  // MAP head
+  float* map_q = nullptr;  // [D] fp32: probe . Wq + bq (input independent)
+  LinearW map_kv, map_out, map_fc1, map_fc2;
+  LNW map_ln;
+  // head after pooling (classifier / visual_projection); N == 0 -> none
+  LinearW head;
+  GemmPlan p_patch, p_head, p_map_kv, p_map_out, p_map_fc1, p_map_fc2;
+};
+
+struct TextTower {
+  bool present = false;
+  int T = 0, V = 0, D = 0, pool = 0;
+  float eps_outer = 1e-5f;
+  Encoder enc;
+  float* table = nullptr;  // [V, D] fp32
+  float* pos = nullptr;    // [T, D] fp32
+  LNW ln_final;
+  LinearW head;  // text_projection
+  GemmPlan p_head;
+};
+
+struct Workspace {
+  float* x = nullptr;     // fp32 residual stream [Tmax, Dmax]
+  void* h = nullptr;      // LN out / attention out (compute dtype) [Tmax, Dmax]
+  void* big = nullptr;    // patches | qkv | mlp hidden | MAP kv (aliased; disjoint lifetimes)
+  void* pooled = nullptr; // [Bmax, Dmax] compute dtype
+  float* feat = nullptr;  // [Bmax, Dmax] fp32 (MAP attention out-proj / residual)
+  void* mid2 = nullptr;   // [Bmax, 4*Dmax] compute dtype (MAP MLP hidden)
+  int* idx = nullptr;     // [Bmax]
+  float* emb_i = nullptr; // [Bmax, E] fp32 encoder outputs
+  float* emb_t = nullptr;
+  float* nrm_i = nullptr; // normalised
+  float* nrm_t = nullptr;
+  void* in_img = nullptr; // host-path staging: image batch (fp32 worst case)
+  int32_t* in_ids = nullptr;
+  float* out_dev = nullptr;  // host-path staging for results
+  size_t out_dev_elems = 0;
+};
+
+}  // namespace jimm
+
+using namespace jimm;
+
+struct jimm_model {
+  jimm_config_t cfg;
+  int device = 0;
+  bool finalized = false;
+  int max_batch = 0;
+  int cdt = DT_F16;    // compute dtype of GEMM operands
+  int adt = DT_F16;    // dtype of the qkv / MAP-kv buffers consumed by the attention kernels (16-bit even in fp32 mode)
+  std::map<std::string, HostParam> host;
+  DevPool pool;
+  VisionTower vis;
+  TextTower txt;
+  float* logit_scale = nullptr;
+  float* logit_bias = nullptr;
+  Workspace ws;
+  CommState comm;
+  int epi_mode_16 = 1;  // epilogue store mode for 16-bit no-residual outputs
+  int epi_mode_res = 0; // epilogue store mode for fp32 residual outputs
+  bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
+};
+
+namespace jimm {
+
+static size_t cdt_size(const jimm_model* m) { return dtype_size(m->cdt); }
+
+// ------------------------------------------------------------------------------------------
+// parameter upload / packing helpers (finalize)
+// ------------------------------------------------------------------------------------------
+struct Packer {
+  jimm_model* m;
+  float* stage = nullptr;  // fp32 device staging buffer
+  size_t stage_elems = 0;
+  cudaStream_t stream = 0;
+
+  int ensure_stage(size_t n) {
+    if (n <= stage_elems) return 0;
+    if (stage) { cudaStreamSynchronize(stream); cudaFree(stage); stage = nullptr; }
+    cudaError_t e = cudaMalloc(&stage, n * sizeof(float));
+    if (e != cudaSuccess) { set_last_error("cudaMalloc staging (%zu floats) failed: %s", n, cudaGetErrorString(e)); return JIMM_ENOMEM; }
+    stage_elems = n;
+    return 0;
+  }
+  void done() {
+    if (stage) { cudaStreamSynchronize(stream); cudaFree(stage); stage = nullptr; stage_elems = 0; }
+  }
+
+  HostParam* find(const std::string& name, std::initializer_list<int64_t> shape) {
+    auto it = m->host.find(name);
+    if (it == m->host.end()) {
+      set_last_error("finalize: parameter '%s' was never set (the reference asserts every flax param is visited, models/vit.py:259)", name.c_str());
+      return nullptr;
+    }
+    HostParam& hp = it->second;
+    std::vector<int64_t> want(shape);
+    if (hp.shape != want) {
+      std::string got, exp;
+      for (auto d : hp.shape) got += std::to_string(d) + ",";
+      for (auto d : want) exp += std::to_string(d) + ",";
+      set_last_error("finalize: shape mismatch for '%s': expected (%s) got (%s)", name.c_str(), exp.c_str(), got.c_str());
+      return nullptr;
+    }
+    hp.used = true;
+    return &hp;
+  }
+
+  // fp32 vector/tensor uploaded as is
+  int upload_f32(const std::string& name, std::initializer_list<int64_t> shape, float** out) {
+    HostParam* hp = find(name, shape);
+    if (!hp) return JIMM_ESTATE;
+    void* d = nullptr;
+    JIMM_TRY(m->pool.alloc(&d, hp->numel() * sizeof(float)));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(d, hp->data.data(), hp->numel() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    *out = static_cast<float*>(d);
+    return 0;
+  }
+  int upload_ln(const std::string& prefix, int D, LNW* ln) {
+    JIMM_TRY(upload_f32(prefix + ".scale", {D}, &ln->scale));
+    JIMM_TRY(upload_f32(prefix + ".bias", {D}, &ln->bias));
+    return 0;
+  }
+  // flax kernel viewed as (K, N) row-major  ->  rows [n0, n0+N) of a packed [Ntot, K] K-major operand
+  int pack_kernel(const std::string& name, std::initializer_list<int64_t> shape, int K, int N, void* dst_base, int n0) {
+    HostParam* hp = find(name, shape);
+    if (!hp) return JIMM_ESTATE;
+    if (hp->numel() != static_cast<size_t>(K) * N) { set_last_error("finalize: '%s' numel mismatch", name.c_str()); return JIMM_ESTATE; }
+    JIMM_TRY(ensure_stage(hp->numel()));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(stage, hp->data.data(), hp->numel() * sizeof(float), cudaMemcpyHostToDevice, stream));
+    uint8_t* dst = static_cast<uint8_t*>(dst_base) + static_cast<size_t>(n0) * K * cdt_size(m);
+    JIMM_TRY(transpose_cast_run(stage, K, N, dst, m->cdt, K, stream));
+    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int alloc_linear(LinearW* lw, int N, int K, bool bias) {
+    lw->N = N; lw->K = K;
+    JIMM_TRY(m->pool.alloc(&lw->w, static_cast<size_t>(N) * K * cdt_size(m)));
+    if (bias) {
+      void* b = nullptr;
+      JIMM_TRY(m->pool.alloc(&b, static_cast<size_t>(N) * sizeof(float)));
+      lw->b = static_cast<float*>(b);
+    }
+    return 0;
+  }
+  int upload_bias_at(const std::string& name, std::initializer_list<int64_t> shape, float* dst, size_t count) {
+    HostParam* hp = find(name, shape);
+    if (!hp) return JIMM_ESTATE;
+    if (hp->numel() != count) { set_last_error("finalize: '%s' numel mismatch", name.c_str()); return JIMM_ESTATE; }
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, hp->data.data(), count * sizeof(float), cudaMemcpyHostToDevice, stream));
+    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  // nnx.Linear: kernel (K,N), optional bias (N)
+  int linear(const std::string& prefix, int K, int N, bool bias, LinearW* lw) {
+    JIMM_TRY(alloc_linear(lw, N, K, bias));
+    JIMM_TRY(pack_kernel(prefix + ".kernel", {K, N}, K, N, lw->w, 0));
+    if (bias) JIMM_TRY(upload_bias_at(prefix + ".bias", {N}, lw->b, N));
+    return 0;
+  }
+  // nnx.MultiHeadAttention projections -> fused operand; names: subset of {"query","key","value"}
+  int fused_proj(const std::string& attn_prefix, const std::vector<std::string>& names, int D, int H, LinearW* lw) {
+    const int d = D / H;
+    const int N = D * static_cast<int>(names.size());
+    JIMM_TRY(alloc_linear(lw, N, D, true));
+    for (size_t i = 0; i < names.size(); ++i) {
+      JIMM_TRY(pack_kernel(attn_prefix + "." + names[i] + ".kernel", {D, H, d}, D, D, lw->w, static_cast<int>(i) * D));
+      JIMM_TRY(upload_bias_at(attn_prefix + "." + names[i] + ".bias", {H, d}, lw->b + i * D, D));
+    }
+    return 0;
+  }
+  int out_proj(const std::string& attn_prefix, int D, int H, LinearW* lw) {
+    const int d = D / H;
+    JIMM_TRY(alloc_linear(lw, D, D, true));
+    JIMM_TRY(pack_kernel(attn_prefix + ".out.kernel", {H, d, D}, D, D, lw->w, 0));
+    JIMM_TRY(upload_bias_at(attn_prefix + ".out.bias", {D}, lw->b, D));
+    return 0;
+  }
+  int encoder(const std::string& prefix, Encoder* enc) {
+    const EncoderCfg& c = enc->c;
+    enc->blocks.resize(c.L);
+    for (int i = 0; i < c.L; ++i) {
+      const std::string f = prefix + "blocks.layers." + std::to_string(i) + ".";
+      BlockW& b = enc->blocks[i];
+      JIMM_TRY(upload_ln(f + "norm1", c.D, &b.norm1));
+      JIMM_TRY(upload_ln(f + "norm2", c.D, &b.norm2));
+      JIMM_TRY(fused_proj(f + "attn", {"query", "key", "value"}, c.D, c.H, &b.qkv));
+      JIMM_TRY(out_proj(f + "attn", c.D, c.H, &b.out));
+      JIMM_TRY(linear(f + "mlp.layers.0", c.D, c.M, true, &b.fc1));
+      JIMM_TRY(linear(f + "mlp.layers.3", c.M, c.D, true, &b.fc2));
+    }
+    return 0;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// GEMM dispatch (plan-based tcgen05 path; optional SIMT bisection path)
+// ------------------------------------------------------------------------------------------
+static int run_gemm(jimm_model* m, const GemmPlan& p, const void* A, int lda, const LinearW& w, int M, cudaStream_t s) {
+  if (M <= 0) return 0;
+  if (m->simt) return gemm_simt_run(p.dtype, A, lda, w.w, w.K, M, p.N, p.K, p.epi, s);
+  return gemm_plan_run(&p, M, s);
+}
+
+static GemmEpilogue epi_plain(const LinearW& w, int act, void* out, int out_type, int ldo, int mode) {
+  GemmEpilogue e;
+  e.bias = w.b; e.act = act; e.out = out; e.out_type = out_type; e.ldo = ldo; e.mode = mode;
+  return e;
+}
+static GemmEpilogue epi_residual(const LinearW& w, float* x, int ld, int mode) {
+  GemmEpilogue e;
+  e.bias = w.b; e.residual = x; e.ldr = ld; e.out = x; e.out_type = DT_F32; e.ldo = ld; e.mode = mode;
+  return e;
+}
+
+static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax) {
+  const EncoderCfg& c = enc->c;
+  Workspace& ws = m->ws;
+  const int act = c.act == JIMM_QUICK_GELU ? ACT_QUICK_GELU : ACT_GELU_TANH;
+  for (BlockW& b : enc->blocks) {
+    // QKV: h[T,D] x Wqkv[3D,D]^T + b -> qkv (16-bit) [T,3D]
+    JIMM_TRY(gemm_plan_init(&b.p_qkv, m->cdt, ws.h, c.D, b.qkv.w, c.D, Tmax, 3 * c.D, c.D,
+                            epi_plain(b.qkv, ACT_NONE, ws.big, m->adt, 3 * c.D, m->epi_mode_16)));
+    // out-proj: attn[T,D] x Wo[D,D]^T + bo + x -> x
+    JIMM_TRY(gemm_plan_init(&b.p_out, m->cdt, ws.h, c.D, b.out.w, c.D, Tmax, c.D, c.D, epi_residual(b.out, ws.x, c.D, m->epi_mode_res)));
+    // FC1: h x W1^T + b1 -> act -> mid [T,M]
+    JIMM_TRY(gemm_plan_init(&b.p_fc1, m->cdt, ws.h, c.D, b.fc1.w, c.D, Tmax, c.M, c.D,
+                            epi_plain(b.fc1, act, ws.big, m->cdt, c.M, m->cdt == DT_F32 ? 0 : m->epi_mode_16)));
+    // FC2: mid x W2^T + b2 + x -> x
+    JIMM_TRY(gemm_plan_init(&b.p_fc2, m->cdt, ws.big, c.M, b.fc2.w, c.M, Tmax, c.D, c.M, epi_residual(b.fc2, ws.x, c.D, m->epi_mode_res)));
+  }
+  return 0;
+}
+
+// x: fp32 [B*S, D] residual stream in ws.x.  TransformerEncoder.__call__ x L (common/transformer.py:116-132,190-196).
+static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s) {
+  const EncoderCfg& c = enc->c;
+  Workspace& ws = m->ws;
+  const int T = B * S;
+  for (BlockW& b : enc->blocks) {
+    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm1.scale, b.norm1.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s));
+    JIMM_TRY(run_gemm(m, b.p_qkv, ws.h, c.D, b.qkv, T, s));
+    JIMM_TRY(attention_run(ws.big, m->adt, ws.h, m->cdt, B, S, c.H, c.causal, s));
+    JIMM_TRY(run_gemm(m, b.p_out, ws.h, c.D, b.out, T, s));
+    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm2.scale, b.norm2.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s));
+    JIMM_TRY(run_gemm(m, b.p_fc1, ws.h, c.D, b.fc1, T, s));
+    JIMM_TRY(run_gemm(m, b.p_fc2, ws.big, c.M, b.fc2, T, s));
+  }
+  return 0;
+}
+
+// VisionTransformerBase.__call__ (common/vit.py:216-248) + the model's head.  out: fp32 [B, out_dim]
+static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float* out, cudaStream_t s) {
+  VisionTower& v = m->vis;
+  Workspace& ws = m->ws;
+  const int D = v.D, S = v.S, n = v.n;
+  // patch embed + pos (+cls)
+  JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s));
+  JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * n, s));
+  if (v.pooling == JIMM_POOL_CLS) JIMM_TRY(cls_row_run(ws.x, v.cls, v.pos, B, S, D, s));
+  if (v.pre_norm) JIMM_TRY(layernorm_run(ws.x, D, 1, 0, nullptr, v.ln_pre.scale, v.ln_pre.bias, v.eps_outer, ws.x, DT_F32, D, B * S, D, s));
+  JIMM_TRY(run_encoder(m, &v.enc, B, S, s));
+  if (v.pooling == JIMM_POOL_CLS) {
+    // ln_post is per-row, only row 0 of each sample is consumed (common/vit.py:244-246)
+    if (v.head.N > 0) {
+      JIMM_TRY(layernorm_run(ws.x, D, S, 0, nullptr, v.ln_post.scale, v.ln_post.bias, v.eps_outer, ws.pooled, m->cdt, D, B, D, s));
+      GemmPlan p = v.p_head;
+      p.epi.out = out;
+      JIMM_TRY(run_gemm(m, p, ws.pooled, D, v.head, B, s));
+    } else {
+      JIMM_TRY(layernorm_run(ws.x, D, S, 0, nullptr, v.ln_post.scale, v.ln_post.bias, v.eps_outer, out, DT_F32, D, B, D, s));
+    }
+    return 0;
+  }
+  // MAP head (common/vit.py:87-101)
+  const int T = B * S;
+  JIMM_TRY(layernorm_run(ws.x, D, 1, 0, nullptr, v.ln_post.scale, v.ln_post.bias, v.eps_outer, ws.h, m->cdt, D, T, D, s));
+  JIMM_TRY(run_gemm(m, v.p_map_kv, ws.h, D, v.map_kv, T, s));                                        // k | v  [T, 2D]
+  JIMM_TRY(map_attention_run(v.map_q, ws.big, m->adt, ws.pooled, m->cdt, B, S, v.enc.c.H, s));     // [B, D]
+  JIMM_TRY(run_gemm(m, v.p_map_out, ws.pooled, D, v.map_out, B, s));                                 // -> feat fp32 [B, D]
+  JIMM_TRY(layernorm_run(ws.feat, D, 1, 0, nullptr, v.map_ln.scale, v.map_ln.bias, v.eps_outer, ws.pooled, m->cdt, D, B, D, s));
+  JIMM_TRY(run_gemm(m, v.p_map_fc1, ws.pooled, D, v.map_fc1, B, s));                                 // gelu -> mid2 [B, 4D]
+  {
+    GemmPlan p = v.p_map_fc2;  // + bias + residual(feat) -> out fp32 [B, D]
+    p.epi.out = out;
+    JIMM_TRY(run_gemm(m, p, ws.mid2, 4 * D, v.map_fc2, B, s));
+  }
+  return 0;
+}
+
+// CLIP.encode_text (models/clip.py:148-167) / SigLIP.encode_text (models/siglip.py:135-153).  out fp32 [B, Dt]
+static int run_text(jimm_model* m, const int32_t* ids, int B, int T, float* out, cudaStream_t s) {
+  TextTower& t = m->txt;
+  Workspace& ws = m->ws;
+  JIMM_TRY(embed_run(ids, t.table, t.pos, ws.x, B, T, t.D, t.V, s));
+  JIMM_TRY(run_encoder(m, &t.enc, B, T, s));
+  if (t.pool == JIMM_TPOOL_EOT_ARGMAX) {
+    JIMM_TRY(argmax_ids_run(ids, ws.idx, B, T, s));
+    JIMM_TRY(layernorm_run(ws.x, t.D, T, 0, ws.idx, t.ln_final.scale, t.ln_final.bias, t.eps_outer, ws.pooled, m->cdt, t.D, B, t.D, s));
+  } else {
+    JIMM_TRY(layernorm_run(ws.x, t.D, T, T - 1, nullptr, t.ln_final.scale, t.ln_final.bias, t.eps_outer, ws.pooled, m->cdt, t.D, B, t.D, s));
+  }
+  GemmPlan p = t.p_head;
+  p.epi.out = out;
+  JIMM_TRY(run_gemm(m, p, ws.pooled, t.D, t.head, B, s));
+  return 0;
+}
+
+static int check_ready(const jimm_model* m, int B) {
+  if (!m) { set_last_error("null model"); return JIMM_EINVAL; }
+  if (!m->finalized) { set_last_error("model not finalized"); return JIMM_ESTATE; }
+  if (B < 0) { set_last_error("negative batch"); return JIMM_EINVAL; }
+  return 0;
+}
+static int set_device(const jimm_model* m) {
+  JIMM_CUDA_CHECK(cudaSetDevice(m->device));
+  return 0;
+}
+
+static int vision_out_dim(const jimm_model* m) { return m->vis.head.N > 0 ? m->vis.head.N : m->vis.D; }
+
+}  // namespace jimm
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+const char* jimm_last_error(void) { return g_err; }
+int jimm_abi_version(void) { return 1; }
+long long jimm_launch_count(void) { return g_launches.load(); }
+
+int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) {
+  if (!cfg || !out) { set_last_error("jimm_model_create: null argument"); return JIMM_EINVAL; }
+  if (cfg->kind < JIMM_VIT || cfg->kind > JIMM_TOWER) { set_last_error("bad kind %d", cfg->kind); return JIMM_EINVAL; }
+  if (cfg->pooling != JIMM_POOL_CLS && cfg->pooling != JIMM_POOL_MAP) {
+    set_last_error("pooling_type must be either MAP or CLS.");  // common/vit.py:178
+    return JIMM_EINVAL;
+  }
+  if (cfg->v_heads <= 0 || cfg->v_width != cfg->v_heads * 64) {
+    set_last_error("vision head_dim must be 64 (width %d, heads %d): the attention kernels are specialised for it", cfg->v_width, cfg->v_heads);
+    return JIMM_EINVAL;
+  }
+  const bool dual = cfg->kind == JIMM_CLIP || cfg->kind == JIMM_SIGLIP;
+  if (dual && (cfg->t_heads <= 0 || cfg->t_width != cfg->t_heads * 64)) {
+    set_last_error("text head_dim must be 64 (width %d, heads %d)", cfg->t_width, cfg->t_heads);
+    return JIMM_EINVAL;
+  }
+  if (cfg->compute_dtype < JIMM_F32 || cfg->compute_dtype > JIMM_BF16) { set_last_error("bad compute_dtype"); return JIMM_EINVAL; }
+  if (cfg->patch <= 0 || cfg->img_size < cfg->patch || (cfg->patch * cfg->in_ch) % 4 != 0) {
+    set_last_error("unsupported patch/img/channels (%d/%d/%d): patch*channels must be a multiple of 4", cfg->patch, cfg->img_size, cfg->in_ch);
+    return JIMM_EINVAL;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_last_error("no CUDA device available (%s): jimm_b200 has no CPU fallback", cudaGetErrorString(e));
+    return JIMM_ECUDA;
+  }
+  if (device < 0 || device >= ndev) { set_last_error("bad device %d (have %d)", device, ndev); return JIMM_EINVAL; }
+  cudaDeviceProp prop;
+  JIMM_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_last_error("device %d is sm_%d%d; jimm_b200 kernels are sm_100a only", device, prop.major, prop.minor);
+    return JIMM_ECUDA;
+  }
+  jimm_model* m = new jimm_model();
+  m->cfg = *cfg;
+  m->device = device;
+  m->cdt = cfg->compute_dtype;
+  m->adt = cfg->compute_dtype == JIMM_BF16 ? DT_BF16 : DT_F16;
+  const char* env = getenv("JIMM_GEMM_IMPL");
+  m->simt = env && strcmp(env, "simt") == 0;
+  if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env) ? 1 : 0;
+  if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env) ? 1 : 0;
+  *out = m;
+  return 0;
+}
+
+int jimm_model_set_param(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype) {
+  if (!m || !flax_path || !host || (ndim > 0 && !shape)) { set_last_error("jimm_model_set_param: null argument"); return JIMM_EINVAL; }
+  if (m->finalized) { set_last_error("model already finalized"); return JIMM_ESTATE; }
+  HostParam hp;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] < 0) { set_last_error("negative dim"); return JIMM_EINVAL; }
+    hp.shape.push_back(shape[i]);
+    n *= static_cast<size_t>(shape[i]);
+  }
+  hp.data.resize(n);
+  if (dtype == JIMM_F32) {
+    memcpy(hp.data.data(), host, n * sizeof(float));
+  } else if (dtype == JIMM_F16) {
+    const __half* h = static_cast<const __half*>(host);
+    for (size_t i = 0; i < n; ++i) hp.data[i] = __half2float(h[i]);
+  } else if (dtype == JIMM_BF16) {
+    const uint16_t* h = static_cast<const uint16_t*>(host);
+    for (size_t i = 0; i < n; ++i) {
+      uint32_t u = static_cast<uint32_t>(h[i]) << 16;
+      memcpy(&hp.data[i], &u, 4);
+    }
+  } else {
+    set_last_error("set_param: unsupported dtype %d", dtype);
+    return JIMM_EINVAL;
+  }
+  m->host[flax_path] = std::move(hp);
+  return 0;
+}
+
+int jimm_model_finalize(jimm_model_t* m, int max_batch) {
+  if (!m) { set_last_error("null model"); return JIMM_EINVAL; }
+  if (m->finalized) { set_last_error("model already finalized"); return JIMM_ESTATE; }
+  if (max_batch <= 0) { set_last_error("max_batch must be positive"); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  const jimm_config_t& c = m->cfg;
+  const bool dual = c.kind == JIMM_CLIP || c.kind == JIMM_SIGLIP;
+  const std::string vp = c.kind == JIMM_VIT ? "encoder." : (dual ? "vision_model." : "");
+  Packer pk{m};
+  int rc = 0;
+  auto fail = [&](int code) { pk.done(); return code; };
+
+  // ---- vision tower ----
+  VisionTower& v = m->vis;
+  v.present = true;
+  v.img = c.img_size; v.P = c.patch; v.C = c.in_ch; v.D = c.v_width;
+  v.n = (c.img_size / c.patch) * (c.img_size / c.patch);
+  v.pooling = c.pooling; v.pre_norm = c.pre_norm; v.patch_bias = c.patch_bias; v.eps_outer = c.v_eps_outer;
+  v.S = v.n + (v.pooling == JIMM_POOL_CLS ? 1 : 0);
+  v.enc.c.D = c.v_width; v.enc.c.H = c.v_heads; v.enc.c.M = c.v_mlp; v.enc.c.L = c.v_layers;
+  v.enc.c.act = c.v_act; v.enc.c.causal = 0; v.enc.c.eps = c.v_eps_block;
+  const int D = v.D, PPC = c.patch * c.patch * c.in_ch;
+  if (PPC % 8 != 0 || D % 8 != 0 || c.v_mlp % 8 != 0) { set_last_error("dims must be multiples of 8"); return JIMM_EINVAL; }
+  if ((rc = pk.alloc_linear(&v.patch, D, PPC, c.patch_bias != 0))) return fail(rc);
+  if ((rc = pk.pack_kernel(vp + "patch_embeddings.kernel", {c.patch, c.patch, c.in_ch, D}, PPC, D, v.patch.w, 0))) return fail(rc);
+  if (c.patch_bias && (rc = pk.upload_bias_at(vp + "patch_embeddings.bias", {D}, v.patch.b, D))) return fail(rc);
+  if (v.pooling == JIMM_POOL_CLS && (rc = pk.upload_f32(vp + "cls_token", {1, 1, D}, &v.cls))) return fail(rc);
+  if ((rc = pk.upload_f32(vp + "position_embeddings", {1, v.S, D}, &v.pos))) return fail(rc);
+  if (c.pre_norm && (rc = pk.upload_ln(vp + "ln_pre", D, &v.ln_pre))) return fail(rc);
+  if ((rc = pk.upload_ln(vp + "ln_post", D, &v.ln_post))) return fail(rc);
+  if ((rc = pk.encoder(vp + "transformer.", &v.enc))) return fail(rc);
+  if (v.pooling == JIMM_POOL_MAP) {
+    const std::string mp = vp + "MAPHead.";
+    const int H = c.v_heads, d = D / H;
+    if ((rc = pk.fused_proj(mp + "attn", {"key", "value"}, D, H, &v.map_kv))) return fail(rc);
+    if ((rc = pk.out_proj(mp + "attn", D, H, &v.map_out))) return fail(rc);
+    if ((rc = pk.upload_ln(mp + "layernorm", D, &v.map_ln))) return fail(rc);
+    if ((rc = pk.linear(mp + "mlp.layers.0", D, 4 * D, true, &v.map_fc1))) return fail(rc);  // intermediate_size = 4*hidden (common/vit.py:175)
+    if ((rc = pk.linear(mp + "mlp.layers.2", 4 * D, D, true, &v.map_fc2))) return fail(rc);
+    // probe query is input independent: q = probe . Wq + bq  (common/vit.py:96-97), done once on the host in fp64
+    HostParam* probe = pk.find(mp + "probe", {1, 1, D});
+    HostParam* wq = pk.find(mp + "attn.query.kernel", {D, H, d});
+    HostParam* bq = pk.find(mp + "attn.query.bias", {H, d});
+    if (!probe || !wq || !bq) return fail(JIMM_ESTATE);
+    std::vector<float> q(D);
+    for (int o = 0; o < D; ++o) {
+      double acc = bq->data[o];
+      for (int i = 0; i < D; ++i) acc += static_cast<double>(probe->data[i]) * wq->data[static_cast<size_t>(i) * D + o];
+      q[o] = static_cast<float>(acc);
+    }
+    void* dq = nullptr;
+    if ((rc = m->pool.alloc(&dq, D * sizeof(float)))) return fail(rc);
+    cudaMemcpy(dq, q.data(), D * sizeof(float), cudaMemcpyHostToDevice);
+    v.map_q = static_cast<float*>(dq);
+  }
+  if (c.kind == JIMM_VIT && c.num_classes > 0) {
+    if (c.num_classes % 4 != 0) { set_last_error("num_classes must be a multiple of 4 (got %d)", c.num_classes); return fail(JIMM_EINVAL); }
+    if ((rc = pk.linear("classifier", D, c.num_classes, true, &v.head))) return fail(rc);
+  } else if (c.kind == JIMM_CLIP) {
+    if ((rc = pk.linear("visual_projection", D, c.t_width, false, &v.head))) return fail(rc);
+  }
+
+  // ---- text tower ----
+  TextTower& t = m->txt;
+  if (dual) {
+    t.present = true;
+    t.T = c.ctx_len; t.V = c.vocab; t.D = c.t_width; t.pool = c.t_pool; t.eps_outer = c.t_eps_outer;
+    t.enc.c.D = c.t_width; t.enc.c.H = c.t_heads; t.enc.c.M = c.t_mlp; t.enc.c.L = c.t_layers;
+    t.enc.c.act = c.t_act; t.enc.c.causal = c.t_causal; t.enc.c.eps = c.t_eps_block;
+    if (t.D % 8 != 0 || c.t_mlp % 8 != 0) { set_last_error("text dims must be multiples of 8"); return fail(JIMM_EINVAL); }
+    if ((rc = pk.upload_f32("token_embedding.embedding", {t.V, t.D}, &t.table))) return fail(rc);
+    if ((rc = pk.upload_f32("positional_embedding", {t.T, t.D}, &t.pos))) return fail(rc);
+    if ((rc = pk.upload_ln("ln_final", t.D, &t.ln_final))) return fail(rc);
+    if ((rc = pk.encoder("text_model.", &t.enc))) return fail(rc);
+    if ((rc = pk.linear("text_projection", t.D, t.D, c.t_head_bias != 0, &t.head))) return fail(rc);
+    if ((rc = pk.upload_f32("logit_scale", {}, &m->logit_scale))) return fail(rc);
+    if (c.kind == JIMM_SIGLIP && (rc = pk.upload_f32("logit_bias", {}, &m->logit_bias))) return fail(rc);
+  }
+  pk.done();
+  for (auto& kv : m->host) {
+    if (!kv.second.used) {
+      set_last_error("finalize: unexpected parameter '%s' was set but is not part of this model", kv.first.c_str());
+      return JIMM_ESTATE;
+    }
+  }
+  m->host.clear();
+
+  // ---- workspace ----
+  Workspace& ws = m->ws;
+  const size_t cs = cdt_size(m);
+  const size_t Bm = max_batch;
+  size_t Tv = Bm * v.S, Dmax = D, x_elems = Tv * D, big_bytes = 0;
+  auto upd = [&](size_t b) { if (b > big_bytes) big_bytes = b; };
+  upd(Bm * v.n * PPC * cs);              // patches
+  upd(Tv * 3 * D * 2);                   // qkv (16-bit)
+  upd(Tv * static_cast<size_t>(c.v_mlp) * cs);  // MLP hidden
+  if (v.pooling == JIMM_POOL_MAP) upd(Tv * 2 * D * 2);
+  if (dual) {
+    const size_t Tt = Bm * t.T;
+    if (Tt * t.D > x_elems) x_elems = Tt * t.D;
+    if (static_cast<size_t>(t.D) > Dmax) Dmax = t.D;
+    upd(Tt * 3 * t.D * 2);
+    upd(Tt * static_cast<size_t>(c.t_mlp) * cs);
+  }
+  const size_t E = dual ? t.D : vision_out_dim(m);
+  void* p = nullptr;
+  if ((rc = m->pool.alloc(&p, x_elems * sizeof(float)))) return rc; ws.x = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&ws.h, x_elems * cs))) return rc;
+  if ((rc = m->pool.alloc(&ws.big, big_bytes))) return rc;
+  if ((rc = m->pool.alloc(&ws.pooled, Bm * Dmax * cs))) return rc;
+  if ((rc = m->pool.alloc(&p, Bm * Dmax * sizeof(float)))) return rc; ws.feat = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&ws.mid2, Bm * 4 * Dmax * cs))) return rc;
+  if ((rc = m->pool.alloc(&p, Bm * sizeof(int)))) return rc; ws.idx = static_cast<int*>(p);
+  if ((rc = m->pool.alloc(&p, Bm * E * sizeof(float)))) return rc; ws.emb_i = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&p, Bm * E * sizeof(float)))) return rc; ws.emb_t = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&p, Bm * E * sizeof(float)))) return rc; ws.nrm_i = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&p, Bm * E * sizeof(float)))) return rc; ws.nrm_t = static_cast<float*>(p);
+  if ((rc = m->pool.alloc(&ws.in_img, Bm * v.img * v.img * v.C * sizeof(float)))) return rc;
+  if (dual) { if ((rc = m->pool.alloc(&p, Bm * t.T * sizeof(int32_t)))) return rc; ws.in_ids = static_cast<int32_t*>(p); }
+  ws.out_dev_elems = dual ? Bm * Bm : Bm * vision_out_dim(m);
+  if (ws.out_dev_elems < Bm * E) ws.out_dev_elems = Bm * E;
+  if ((rc = m->pool.alloc(&p, ws.out_dev_elems * sizeof(float)))) return rc; ws.out_dev = static_cast<float*>(p);
+
+  // ---- GEMM plans (TMA descriptors bound to the fixed workspace / weight buffers) ----
+  {
+    GemmEpilogue e;
+    e.bias = v.patch.b; e.rowadd = v.pos; e.out = ws.x; e.out_type = DT_F32; e.ldo = D;
+    e.rows_in = v.n; e.rows_out = v.S; e.row_off = v.pooling == JIMM_POOL_CLS ? 1 : 0; e.mode = 0;
+    JIMM_TRY(gemm_plan_init(&v.p_patch, m->cdt, ws.big, PPC, v.patch.w, PPC, static_cast<int>(Bm) * v.n, D, PPC, e));
+  }
+  JIMM_TRY(plan_encoder(m, &v.enc, static_cast<int>(Tv)));
+  if (v.head.N > 0)
+    JIMM_TRY(gemm_plan_init(&v.p_head, m->cdt, ws.pooled, D, v.head.w, D, static_cast<int>(Bm), v.head.N, D,
+                            epi_plain(v.head, ACT_NONE, ws.out_dev, DT_F32, v.head.N, 0)));
+  if (v.pooling == JIMM_POOL_MAP) {
+    JIMM_TRY(gemm_plan_init(&v.p_map_kv, m->cdt, ws.h, D, v.map_kv.w, D, static_cast<int>(Tv), 2 * D, D,
+                            epi_plain(v.map_kv, ACT_NONE, ws.big, m->adt, 2 * D, m->epi_mode_16)));
+    JIMM_TRY(gemm_plan_init(&v.p_map_out, m->cdt, ws.pooled, D, v.map_out.w, D, static_cast<int>(Bm), D, D,
+                            epi_plain(v.map_out, ACT_NONE, ws.feat, DT_F32, D, 0)));
+    JIMM_TRY(gemm_plan_init(&v.p_map_fc1, m->cdt, ws.pooled, D, v.map_fc1.w, D, static_cast<int>(Bm), 4 * D, D,
+                            epi_plain(v.map_fc1, ACT_GELU_TANH, ws.mid2, m->cdt, 4 * D, 0)));
+    GemmEpilogue e = epi_plain(v.map_fc2, ACT_NONE, ws.out_dev, DT_F32, D, 0);
+    e.residual = ws.feat; e.ldr = D;
+    JIMM_TRY(gemm_plan_init(&v.p_map_fc2, m->cdt, ws.mid2, 4 * D, v.map_fc2.w, 4 * D, static_cast<int>(Bm), D, 4 * D, e));
+  }
+  if (dual) {
+    JIMM_TRY(plan_encoder(m, &t.enc, static_cast<int>(Bm) * t.T));
+    JIMM_TRY(gemm_plan_init(&t.p_head, m->cdt, ws.pooled, t.D, t.head.w, t.D, static_cast<int>(Bm), t.D, t.D,
+                            epi_plain(t.head, ACT_NONE, ws.out_dev, DT_F32, t.D, 0)));
+  }
+  JIMM_CUDA_CHECK(cudaDeviceSynchronize());
+  m->max_batch = max_batch;
+  m->finalized = true;
+  return 0;
+}
+
+int jimm_model_destroy(jimm_model_t* m) {
+  if (!m) return 0;
+  cudaSetDevice(m->device);
+  cudaDeviceSynchronize();
+  comm_destroy(&m->comm);
+  m->pool.release();
+  delete m;
+  return 0;
+}
+
+int jimm_model_output_dim(const jimm_model_t* m, int* vision_out, int* text_out) {
+  if (!m) { set_last_error("null model"); return JIMM_EINVAL; }
+  if (vision_out) *vision_out = m->cfg.kind == JIMM_VIT && m->cfg.num_classes > 0 ? m->cfg.num_classes
+                                : (m->cfg.kind == JIMM_CLIP ? m->cfg.t_width : m->cfg.v_width);
+  if (text_out) *text_out = m->cfg.t_width;
+  return 0;
+}
+int jimm_model_max_batch(const jimm_model_t* m) { return m ? m->max_batch : 0; }
+
+// ---- forward, device buffers ----
+static int vision_chunks(jimm_model* m, const void* img, int in_dtype, int B, float* out, cudaStream_t s) {
+  const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
+  const size_t in_es = dtype_size(in_dtype);
+  const int od = vision_out_dim(m);
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    JIMM_TRY(run_vision(m, static_cast<const uint8_t*>(img) + b0 * img_elems * in_es, in_dtype, nb, out + static_cast<size_t>(b0) * od, s));
+  }
+  return 0;
+}
+static int text_chunks(jimm_model* m, const int32_t* ids, int B, int T, float* out, cudaStream_t s) {
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    JIMM_TRY(run_text(m, ids + static_cast<size_t>(b0) * T, nb, T, out + static_cast<size_t>(b0) * m->txt.D, s));
+  }
+  return 0;
+}
+
+int jimm_vit_forward(jimm_model_t* m, const void* img, int in_dtype, int B, float* out, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward on a dual-tower model; use jimm_encode_image"); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  return vision_chunks(m, img, in_dtype, B, out, static_cast<cudaStream_t>(stream));
+}
+
+int jimm_encode_image(jimm_model_t* m, const void* img, int in_dtype, int B, float* out, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  return vision_chunks(m, img, in_dtype, B, out, static_cast<cudaStream_t>(stream));
+}
+
+int jimm_encode_text(jimm_model_t* m, const int32_t* ids, int B, int T, float* out, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
+  if (T <= 0 || T > m->txt.T) { set_last_error("sequence length %d outside (0, context_length=%d]", T, m->txt.T); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  return text_chunks(m, ids, B, T, out, static_cast<cudaStream_t>(stream));
+}
+
+int jimm_contrastive_logits(jimm_model_t* m, const float* img_e, int Bi, const float* txt_e, int Bt, float* logits, void* stream) {
+  JIMM_TRY(check_ready(m, Bi));
+  if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
+  if (Bi > m->max_batch || Bt > m->max_batch) { set_last_error("contrastive_logits: batch (%d,%d) exceeds max_batch %d", Bi, Bt, m->max_batch); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int E = m->txt.D;
+  JIMM_TRY(l2_normalize_run(img_e, m->ws.nrm_i, E, Bi, E, s));
+  JIMM_TRY(l2_normalize_run(txt_e, m->ws.nrm_t, E, Bt, E, s));
+  return logits_run(m->ws.nrm_i, m->ws.nrm_t, m->logit_scale, m->logit_bias, logits, Bi, Bt, E, Bt, s);
+}
+
+int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* logits,
+                      void* stream) {
+  JIMM_TRY(check_ready(m, Bi));
+  if (Bi > m->max_batch || Bt > m->max_batch) { set_last_error("dual_forward: batch (%d,%d) exceeds max_batch %d", Bi, Bt, m->max_batch); return JIMM_EINVAL; }
+  JIMM_TRY(jimm_encode_image(m, img, in_dtype, Bi, m->ws.emb_i, stream));
+  JIMM_TRY(jimm_encode_text(m, ids, Bt, T, m->ws.emb_t, stream));
+  return jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, logits, stream);
+}
+
+// ---- forward, host buffers ----
+int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host on a dual-tower model"); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
+  const int od = vision_out_dim(m);
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, static_cast<const uint8_t*>(img_host) + b0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, s));
+    JIMM_TRY(run_vision(m, m->ws.in_img, in_dtype, nb, m->ws.out_dev, s));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  }
+  return 0;
+}
+
+int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int Bi, const int32_t* ids_host, int Bt, int T,
+                           float* logits_host, void* stream) {
+  JIMM_TRY(check_ready(m, Bi));
+  if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
+  if (Bi > m->max_batch || Bt > m->max_batch) { set_last_error("dual_forward_host: batch (%d,%d) exceeds max_batch %d", Bi, Bt, m->max_batch); return JIMM_EINVAL; }
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, img_host, Bi * img_bytes, cudaMemcpyHostToDevice, s));
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids_host, static_cast<size_t>(Bt) * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  JIMM_TRY(jimm_dual_forward(m, m->ws.in_img, in_dtype, Bi, m->ws.in_ids, Bt, T, m->ws.out_dev, stream));
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(logits_host, m->ws.out_dev, static_cast<size_t>(Bi) * Bt * sizeof(float), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
+// ---- multi-GPU contrastive head ----
+int jimm_comm_init(jimm_model_t* m, int rank, int world, int max_rows_per_rank, unsigned char* handle_out) {
+  JIMM_TRY(check_ready(m, 0));
+  if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  return comm_init(&m->comm, rank, world, max_rows_per_rank, m->txt.D, handle_out);
+}
+int jimm_comm_connect(jimm_model_t* m, const unsigned char* handles) {
+  JIMM_TRY(check_ready(m, 0));
+  JIMM_TRY(set_device(m));
+  return comm_connect(&m->comm, handles);
+}
+int jimm_comm_contrastive_logits(jimm_model_t* m, const float* img_e, const float* txt_e, int B_local, float* logits_local, void* stream) {
+  JIMM_TRY(check_ready(m, B_local));
+  JIMM_TRY(set_device(m));
+  return comm_contrastive_logits(&m->comm, img_e, txt_e, B_local, m->logit_scale, m->logit_bias, logits_local, static_cast<cudaStream_t>(stream));
+}
+int jimm_comm_gathered(jimm_model_t* m, float** gathered, int* row_stride) {
+  if (!m || !m->comm.ready) { set_last_error("comm not initialised"); return JIMM_ESTATE; }
+  if (gathered) *gathered = m->comm.local_buf;
+  if (row_stride) *row_stride = 2 * m->comm.E;
+  return 0;
+}
+
+// ---- per-kernel entry points ----
+int jimm_k_gemm(int impl, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K, const float* bias, int act,
+                const float* rowadd, const float* residual, int ldr, void* out, int out_type, int ldo, int rows_in, int rows_out,
+                int row_off, int epi_mode, void* stream) {
+  GemmEpilogue e;
+  e.bias = bias; e.act = act; e.rowadd = rowadd; e.residual = residual; e.ldr = ldr; e.out = out; e.out_type = out_type; e.ldo = ldo;
+  e.rows_in = rows_in; e.rows_out = rows_out; e.row_off = row_off; e.mode = epi_mode;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 1) return gemm_simt_run(dtype, A, lda, B, ldb, M, N, K, e, s);
+  GemmPlan p;
+  JIMM_TRY(gemm_plan_init(&p, dtype, A, lda, B, ldb, M, N, K, e));
+  return gemm_plan_run(&p, M, s);
+}
+int jimm_k_layernorm(const float* x, int ldx, int group, int row_off, const int32_t* row_index, const float* scale, const float* bias,
+                     float eps, void* out, int out_type, int ldy, int rows, int D, void* stream) {
+  return layernorm_run(x, ldx, group, row_off, row_index, scale, bias, eps, out, out_type, ldy, rows, D, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_attention(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, void* stream) {
+  return attention_run(qkv, io_type, out, out_type, B, S, H, causal, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_map_attention(const float* q, const void* kv, int io_type, void* out, int out_type, int B, int S, int H, void* stream) {
+  return map_attention_run(q, kv, io_type, out, out_type, B, S, H, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_patchify(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, void* stream) {
+  return patchify_run(img, in_type, B, H, W, C, P, out, out_type, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_embed(const int32_t* ids, const float* table, const float* pos, float* x, int B, int T, int D, int vocab, void* stream) {
+  return embed_run(ids, table, pos, x, B, T, D, vocab, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_l2_normalize(const float* x, float* out, int ldo, int B, int E, void* stream) {
+  return l2_normalize_run(x, out, ldo, B, E, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_logits(const float* img, const float* txt, const float* logit_scale, const float* logit_bias, float* logits, int Bi, int Bt,
+                  int E, int ldl, void* stream) {
+  return logits_run(img, txt, logit_scale, logit_bias, logits, Bi, Bt, E, ldl, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
