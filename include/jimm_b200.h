@@ -129,6 +129,11 @@ JIMM_API int jimm_k_embed(const int32_t* ids, const float* table, const float* p
 JIMM_API int jimm_k_l2_normalize(const float* x, float* out, int ldo, int B, int E, void* stream);
 JIMM_API int jimm_k_logits(const float* img, const float* txt, const float* logit_scale, const float* logit_bias, float* logits, int Bi, int Bt,
                   int E, int ldl, void* stream);
+/* Live timing of the dominant kernel (the tcgen05 GEMM) inside a forward: between begin and end every GEMM launch is
+ * bracketed by CUDA events on the launch stream; end synchronises and returns the summed device time (ms), the
+ * algorithmic FLOPs (2*M*N*K per launch) and the number of launches.  Used by bench.py's roofline object. */
+JIMM_API int jimm_profile_begin(jimm_model_t* m);
+JIMM_API int jimm_profile_end(jimm_model_t* m, double* gemm_ms, double* gemm_flops, long long* gemm_launches);
 /* Count of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 JIMM_API long long jimm_launch_count(void);
 

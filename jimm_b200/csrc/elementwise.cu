@@ -148,8 +148,8 @@ static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P,
 }
 
 int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream) {
-  if ((P * C) % 4 != 0 || (static_cast<size_t>(H) * W * C) % 4 != 0) {
-    set_last_error("patchify: patch_size*channels (%d) must be a multiple of 4", P * C);
+  if ((P * C) % 4 != 0 || (W * C) % 4 != 0) {
+    set_last_error("patchify: patch_size*channels (%d) and width*channels (%d) must be multiples of 4", P * C, W * C);
     return -1;
   }
   if (B <= 0) return 0;

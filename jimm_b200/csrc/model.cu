@@ -170,6 +170,11 @@ struct jimm_model {
   float* logit_bias = nullptr;
   Workspace ws;
   CommState comm;
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
+  long long prof_launches = 0;
   int epi_mode_16 = 1;  // epilogue store mode for 16-bit no-residual outputs
   int epi_mode_res = 0; // epilogue store mode for fp32 residual outputs
   bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
@@ -313,7 +318,21 @@ struct Packer {
 static int run_gemm(jimm_model* m, const GemmPlan& p, const void* A, int lda, const LinearW& w, int M, cudaStream_t s) {
   if (M <= 0) return 0;
   if (m->simt) return gemm_simt_run(p.dtype, A, lda, w.w, w.K, M, p.N, p.K, p.epi, s);
-  return gemm_plan_run(&p, M, s);
+  if (!m->prof_on) return gemm_plan_run(&p, M, s);
+  if (m->prof_used + 2 > m->prof_ev.size()) {
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      JIMM_CUDA_CHECK(cudaEventCreate(&e));
+      m->prof_ev.push_back(e);
+    }
+  }
+  JIMM_CUDA_CHECK(cudaEventRecord(m->prof_ev[m->prof_used], s));
+  JIMM_TRY(gemm_plan_run(&p, M, s));
+  JIMM_CUDA_CHECK(cudaEventRecord(m->prof_ev[m->prof_used + 1], s));
+  m->prof_used += 2;
+  m->prof_flops += 2.0 * M * static_cast<double>(p.N) * p.K;
+  m->prof_launches += 1;
+  return 0;
 }
 
 static GemmEpilogue epi_plain(const LinearW& w, int act, void* out, int out_type, int ldo, int mode) {
@@ -682,6 +701,7 @@ int jimm_model_destroy(jimm_model_t* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   comm_destroy(&m->comm);
+  for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   m->pool.release();
   delete m;
   return 0;
@@ -814,6 +834,32 @@ int jimm_comm_gathered(jimm_model_t* m, float** gathered, int* row_stride) {
   if (!m || !m->comm.ready) { set_last_error("comm not initialised"); return JIMM_ESTATE; }
   if (gathered) *gathered = m->comm.local_buf;
   if (row_stride) *row_stride = 2 * m->comm.E;
+  return 0;
+}
+
+int jimm_profile_begin(jimm_model_t* m) {
+  JIMM_TRY(check_ready(m, 0));
+  m->prof_on = true;
+  m->prof_used = 0;
+  m->prof_flops = 0.0;
+  m->prof_launches = 0;
+  return 0;
+}
+int jimm_profile_end(jimm_model_t* m, double* gemm_ms, double* gemm_flops, long long* gemm_launches) {
+  JIMM_TRY(check_ready(m, 0));
+  JIMM_TRY(set_device(m));
+  m->prof_on = false;
+  JIMM_CUDA_CHECK(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < m->prof_used; i += 2) {
+    float t = 0.f;
+    JIMM_CUDA_CHECK(cudaEventElapsedTime(&t, m->prof_ev[i], m->prof_ev[i + 1]));
+    ms += t;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = m->prof_flops;
+  if (gemm_launches) *gemm_launches = m->prof_launches;
+  m->prof_used = 0;
   return 0;
 }
 

@@ -1,0 +1,68 @@
+"""Bring-up diagnostic for the tcgen05 GEMM (run on the GPU box): compares against torch and the SIMT kernel and prints a
+block-wise error map so descriptor / swizzle / TMEM-lane mistakes are visible in one round trip."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+
+from gpu_util import gemm, rel_err
+from jimm_b200 import _lib
+
+lib = _lib.load()
+torch.manual_seed(0)
+print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))
+
+
+def run(M, N, K, dtype, mode):
+    A = torch.randn(M, K, device="cuda").to(dtype)
+    B = (torch.randn(N, K, device="cuda") / K ** 0.5).to(dtype)
+    if dtype == torch.float32:
+        A = (A.view(torch.int32) & ~0x1FFF).view(torch.float32)
+        B = (B.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    ref = A.double() @ B.double().T
+    out = gemm(lib, A, B, mode=mode)
+    torch.cuda.synchronize()
+    e = rel_err(out, ref)
+    print(f"M={M} N={N} K={K} {dtype} mode={mode}: rel err {e:.3e}", flush=True)
+    if e > 1e-4:
+        d = (out.double() - ref).abs()
+        bm, bn = min(M, 32), min(N, 32)
+        blk = d[: (M // bm) * bm, : (N // bn) * bn].reshape(M // bm, bm, N // bn, bn).amax(dim=(1, 3))
+        print("block max-abs-error map (32x32 blocks):")
+        print((blk > 1e-3).int()[:8, :16])
+        print("out[0,:8]", out[0, :8].tolist())
+        print("ref[0,:8]", ref[0, :8].tolist())
+        # is it a permutation of columns / rows?
+        for r in (0, 1, 8, 33):
+            if r < M:
+                best = (ref - out[r].double().unsqueeze(0)).abs().amax(dim=1).argmin().item()
+                print(f"out row {r} best matches ref row {best}")
+    return e
+
+
+worst = 0.0
+for dtype in (torch.float16, torch.bfloat16, torch.float32):
+    for (M, N, K) in ((128, 256, 64), (128, 256, 256), (256, 512, 768), (1000, 1000, 512)):
+        for mode in (0, 1):
+            worst = max(worst, run(M, N, K, dtype, mode))
+print("WORST", worst)
+
+# quick perf probe of the big shapes (CUDA events, 10 reps)
+for (M, N, K) in ((50432, 2304, 768), (50432, 3072, 768), (50432, 768, 3072), (50432, 768, 768)):
+    A = torch.randn(M, K, device="cuda").half()
+    B = torch.randn(N, K, device="cuda").half()
+    for mode in (0, 1):
+        out = torch.empty(M, N, device="cuda", dtype=torch.float16)
+        for _ in range(3):
+            gemm(lib, A, B, mode=mode, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gemm(lib, A, B, mode=mode, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"perf M={M} N={N} K={K} f16 out f16 mode={mode}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
