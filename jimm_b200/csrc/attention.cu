@@ -251,6 +251,7 @@ attention_kernel(const T* __restrict__ qkv, OutT* __restrict__ out, int S, int H
         const int srow = row_lo + r * 8;
         if (srow < S) {
           float2 v = make_float2(o[nt][2 * r] * inv[r], o[nt][2 * r + 1] * inv[r]);
+          if constexpr (std::is_same<OutT, tf32_t>::value) v = make_float2(round_tf32(v.x), round_tf32(v.y));
           *reinterpret_cast<float2*>(reinterpret_cast<float*>(obase) + static_cast<size_t>(srow) * D + nt * 8 + t4 * 2) = v;
         }
       }
@@ -273,6 +274,7 @@ int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, 
   if (B > 65535 || H > 65535) { set_last_error("attention: grid too large (B=%d H=%d)", B, H); return -1; }
   if (io_type == DT_F16 && out_type == DT_F16) return attn_launch<__half, __half>(qkv, out, B, S, H, causal, stream);
   if (io_type == DT_F16 && out_type == DT_F32) return attn_launch<__half, float>(qkv, out, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_TF32) return attn_launch<__half, tf32_t>(qkv, out, B, S, H, causal, stream);
   if (io_type == DT_BF16 && out_type == DT_BF16) return attn_launch<__nv_bfloat16, __nv_bfloat16>(qkv, out, B, S, H, causal, stream);
   if (io_type == DT_BF16 && out_type == DT_F32) return attn_launch<__nv_bfloat16, float>(qkv, out, B, S, H, causal, stream);
   set_last_error("attention: unsupported dtype combination io=%d out=%d", io_type, out_type);
@@ -365,6 +367,7 @@ int map_attention_run(const float* q, const void* kv, int io_type, void* out, in
   if (S > 8192) { set_last_error("map_attention: S=%d too large", S); return -1; }
   if (io_type == DT_F16 && out_type == DT_F16) return map_launch<__half, __half>(q, kv, out, B, S, H, stream);
   if (io_type == DT_F16 && out_type == DT_F32) return map_launch<__half, float>(q, kv, out, B, S, H, stream);
+  if (io_type == DT_F16 && out_type == DT_TF32) return map_launch<__half, tf32_t>(q, kv, out, B, S, H, stream);
   if (io_type == DT_BF16 && out_type == DT_BF16) return map_launch<__nv_bfloat16, __nv_bfloat16>(q, kv, out, B, S, H, stream);
   if (io_type == DT_BF16 && out_type == DT_F32) return map_launch<__nv_bfloat16, float>(q, kv, out, B, S, H, stream);
   set_last_error("map_attention: unsupported dtype combination io=%d out=%d", io_type, out_type);

@@ -197,8 +197,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// round-to-nearest tf32 (10 explicit mantissa bits), result kept in an fp32 container
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+struct tf32_t {
+  float v;
+};
+
 template <typename T>
 __device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ tf32_t from_float<tf32_t>(float v) { return tf32_t{round_tf32(v)}; }
 template <>
 __device__ __forceinline__ float from_float<float>(float v) { return v; }
 template <>

@@ -55,7 +55,9 @@ layernorm_kernel(const float* __restrict__ x, size_t ldx, int group, int row_off
       y.y = (v[i].y - mean) * rstd * g.y + b.y;
       y.z = (v[i].z - mean) * rstd * g.z + b.z;
       y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      if constexpr (sizeof(OutT) == 4) {
+      if constexpr (std::is_same<OutT, tf32_t>::value) {
+        reinterpret_cast<float4*>(orow)[idx] = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
+      } else if constexpr (sizeof(OutT) == 4) {
         reinterpret_cast<float4*>(orow)[idx] = y;
       } else {
         uint2 p;
@@ -90,6 +92,7 @@ int layernorm_run(const float* x, int ldx, int group, int row_off, const int* ro
   }
   if (rows <= 0) return 0;
   if (out_type == DT_F32) return ln_launch<float>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
+  if (out_type == DT_TF32) return ln_launch<tf32_t>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
   if (out_type == DT_F16) return ln_launch<__half>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
   return ln_launch<__nv_bfloat16>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
 }
@@ -122,7 +125,9 @@ patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int 
   }
   const size_t dst = (static_cast<size_t>(b) * gh * gw + static_cast<size_t>(gy) * gw + gx) * (static_cast<size_t>(P) * PC) +
                      static_cast<size_t>(ky) * PC + kc;
-  if constexpr (sizeof(OutT) == 4) {
+  if constexpr (std::is_same<OutT, tf32_t>::value) {
+    *reinterpret_cast<float4*>(out + dst) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
+  } else if constexpr (sizeof(OutT) == 4) {
     *reinterpret_cast<float4*>(out + dst) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
     constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
@@ -141,6 +146,7 @@ static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P,
   const unsigned grid = static_cast<unsigned>((total4 + threads - 1) / threads);
   const InT* in = static_cast<const InT*>(img);
   if (out_type == DT_F32) patchify_kernel<InT, float><<<grid, threads, 0, stream>>>(in, static_cast<float*>(out), B, H, W, C, P, gh, gw, total4);
+  else if (out_type == DT_TF32) patchify_kernel<InT, tf32_t><<<grid, threads, 0, stream>>>(in, static_cast<tf32_t*>(out), B, H, W, C, P, gh, gw, total4);
   else if (out_type == DT_F16) patchify_kernel<InT, __half><<<grid, threads, 0, stream>>>(in, static_cast<__half*>(out), B, H, W, C, P, gh, gw, total4);
   else patchify_kernel<InT, __nv_bfloat16><<<grid, threads, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), B, H, W, C, P, gh, gw, total4);
   JIMM_LAUNCH_CHECK();
@@ -280,6 +286,7 @@ __global__ void transpose_cast_kernel(const float* __restrict__ src, int K, int 
 int transpose_cast_run(const float* src, int K, int N, void* dst, int out_type, int ldd, cudaStream_t stream) {
   dim3 block(32, 8), grid((N + 31) / 32, (K + 31) / 32);
   if (out_type == DT_F32) transpose_cast_kernel<float><<<grid, block, 0, stream>>>(src, K, N, static_cast<float*>(dst), ldd);
+  else if (out_type == DT_TF32) transpose_cast_kernel<tf32_t><<<grid, block, 0, stream>>>(src, K, N, static_cast<tf32_t*>(dst), ldd);
   else if (out_type == DT_F16) transpose_cast_kernel<__half><<<grid, block, 0, stream>>>(src, K, N, static_cast<__half*>(dst), ldd);
   else transpose_cast_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(src, K, N, static_cast<__nv_bfloat16*>(dst), ldd);
   JIMM_LAUNCH_CHECK();
@@ -295,6 +302,7 @@ int cast_run(const float* src, void* dst, int out_type, size_t n, cudaStream_t s
   if (n == 0) return 0;
   const unsigned grid = static_cast<unsigned>((n + 255) / 256);
   if (out_type == DT_F32) cast_kernel<float><<<grid, 256, 0, stream>>>(src, static_cast<float*>(dst), n);
+  else if (out_type == DT_TF32) cast_kernel<tf32_t><<<grid, 256, 0, stream>>>(src, static_cast<tf32_t*>(dst), n);
   else if (out_type == DT_F16) cast_kernel<__half><<<grid, 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
   else cast_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
   JIMM_LAUNCH_CHECK();

@@ -44,6 +44,7 @@ struct EpiDev {
   void* out;
   int act, ldr, out_type, ldo, rows_in, rows_out, row_off, mode;
   int M, N;
+  int vec;  // 1: N / ldo / ldr are multiples of 4 (8 for 16-bit direct stores) -> vector accesses allowed
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -68,6 +69,8 @@ __device__ __forceinline__ void store4(const EpiDev& e, int out_row, int col, fl
   size_t off = static_cast<size_t>(out_row) * e.ldo + col;
   if (e.out_type == DT_F32) {
     *reinterpret_cast<float4*>(static_cast<float*>(e.out) + off) = v;
+  } else if (e.out_type == DT_TF32) {
+    *reinterpret_cast<float4*>(static_cast<float*>(e.out) + off) = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
   } else {
     uint2 p;
     p.x = pack2(v.x, v.y, e.out_type);
@@ -78,6 +81,7 @@ __device__ __forceinline__ void store4(const EpiDev& e, int out_row, int col, fl
 __device__ __forceinline__ void store1(const EpiDev& e, int out_row, int col, float v) {
   size_t off = static_cast<size_t>(out_row) * e.ldo + col;
   if (e.out_type == DT_F32) static_cast<float*>(e.out)[off] = v;
+  else if (e.out_type == DT_TF32) static_cast<float*>(e.out)[off] = round_tf32(v);
   else if (e.out_type == DT_F16) static_cast<__half*>(e.out)[off] = __float2half_rn(v);
   else static_cast<__nv_bfloat16*>(e.out)[off] = __float2bfloat16_rn(v);
 }
@@ -215,7 +219,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               int out_row, add_row;
               remap_row(epi, row, out_row, add_row);
               const bool full = (n0 + 32 <= N);
-              if (full && epi.out_type != DT_F32 && epi.rowadd == nullptr && epi.residual == nullptr) {
+              if (full && epi.vec && (epi.out_type == DT_F16 || epi.out_type == DT_BF16) && epi.rowadd == nullptr && epi.residual == nullptr) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
@@ -251,7 +255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             __syncwarp();
             const int cq = (lane & 7) * 4;
             const int col = n0 + cq;
-            const bool col_ok = (col + 3 < N);
+            const bool col_ok = epi.vec && (col + 3 < N);
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (epi.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
 #pragma unroll
@@ -366,7 +370,7 @@ static int make_map(CUtensorMap* map, int dtype, const void* ptr, int rows, int 
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -3;
   const size_t es = dtype_size(dtype);
-  CUtensorMapDataType dt = dtype == DT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+  CUtensorMapDataType dt = (dtype == DT_F32 || dtype == DT_TF32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                            : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * es};
@@ -399,10 +403,17 @@ int device_sm_count() {
 
 static int check_epi(const GemmEpilogue& e, int N) {
   if (e.out == nullptr) { set_last_error("gemm: null output"); return -1; }
-  if (e.ldo % 4 != 0 || N % 4 != 0) { set_last_error("gemm: N (%d) and ldo (%d) must be multiples of 4", N, e.ldo); return -1; }
-  if (e.residual && e.ldr % 4 != 0) { set_last_error("gemm: ldr must be a multiple of 4"); return -1; }
-  if (e.mode == 1 && e.out_type != DT_F32 && e.ldo % 8 != 0) { set_last_error("gemm: direct 16-bit epilogue needs ldo %% 8 == 0"); return -1; }
+  if (e.ldo < N) { set_last_error("gemm: ldo (%d) < N (%d)", e.ldo, N); return -1; }
   return 0;
+}
+// vector accesses need aligned rows; otherwise the epilogue takes its scalar path (tiny head GEMMs such as N = 10 classes)
+static int epi_vec_ok(const GemmEpilogue& e, int N) {
+  const int a = (e.mode == 1 && (e.out_type == DT_F16 || e.out_type == DT_BF16)) ? 8 : 4;
+  if (N % 4 != 0 || e.ldo % a != 0) return 0;
+  if (e.residual && e.ldr % 4 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(e.out) & 15) || (reinterpret_cast<uintptr_t>(e.bias) & 15) ||
+      (reinterpret_cast<uintptr_t>(e.residual) & 15) || (reinterpret_cast<uintptr_t>(e.rowadd) & 15)) return 0;
+  return 1;
 }
 
 int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
@@ -421,6 +432,7 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.act = e.act; d.ldr = e.ldr; d.out_type = e.out_type; d.ldo = e.ldo;
   d.rows_in = e.rows_in; d.rows_out = e.rows_out; d.row_off = e.row_off; d.mode = e.mode;
   d.M = M; d.N = N;
+  d.vec = epi_vec_ok(e, N);
   return d;
 }
 
@@ -443,7 +455,8 @@ int gemm_plan_run(const GemmPlan* p, int M_override, cudaStream_t stream) {
   switch (p->dtype) {
     case DT_F16: return launch_tc<__half>(p, M, stream);
     case DT_BF16: return launch_tc<__nv_bfloat16>(p, M, stream);
-    case DT_F32: return launch_tc<float>(p, M, stream);
+    case DT_F32:
+    case DT_TF32: return launch_tc<float>(p, M, stream);
   }
   set_last_error("gemm: bad dtype %d", p->dtype);
   return -1;

@@ -13,10 +13,12 @@
 
 namespace jimm {
 
-enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2 };
+// DT_TF32: stored as fp32 with the value rounded (to nearest) to tf32 -- the operand format of the fp32 compute mode, so the
+// tensor core's truncation of the low 13 mantissa bits is exact.  Only ever an internal buffer / operand type.
+enum DType : int { DT_F32 = 0, DT_F16 = 1, DT_BF16 = 2, DT_TF32 = 3 };
 enum Act : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_QUICK_GELU = 2 };
 
-inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+inline size_t dtype_size(int dt) { return (dt == DT_F32 || dt == DT_TF32) ? 4 : 2; }
 
 struct GemmEpilogue {
   const float* bias = nullptr;      // [N] fp32, added per output column

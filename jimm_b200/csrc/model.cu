@@ -358,7 +358,7 @@ static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax) {
     JIMM_TRY(gemm_plan_init(&b.p_out, m->cdt, ws.h, c.D, b.out.w, c.D, Tmax, c.D, c.D, epi_residual(b.out, ws.x, c.D, m->epi_mode_res)));
     // FC1: h x W1^T + b1 -> act -> mid [T,M]
     JIMM_TRY(gemm_plan_init(&b.p_fc1, m->cdt, ws.h, c.D, b.fc1.w, c.D, Tmax, c.M, c.D,
-                            epi_plain(b.fc1, act, ws.big, m->cdt, c.M, m->cdt == DT_F32 ? 0 : m->epi_mode_16)));
+                            epi_plain(b.fc1, act, ws.big, m->cdt, c.M, m->cdt == DT_TF32 ? 0 : m->epi_mode_16)));
     // FC2: mid x W2^T + b2 + x -> x
     JIMM_TRY(gemm_plan_init(&b.p_fc2, m->cdt, ws.big, c.M, b.fc2.w, c.M, Tmax, c.D, c.M, epi_residual(b.fc2, ws.x, c.D, m->epi_mode_res)));
   }
@@ -500,7 +500,7 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   jimm_model* m = new jimm_model();
   m->cfg = *cfg;
   m->device = device;
-  m->cdt = cfg->compute_dtype;
+  m->cdt = cfg->compute_dtype == JIMM_F32 ? DT_TF32 : cfg->compute_dtype;  // fp32 mode: operands rounded to tf32 when produced
   m->adt = cfg->compute_dtype == JIMM_BF16 ? DT_BF16 : DT_F16;
   const char* env = getenv("JIMM_GEMM_IMPL");
   m->simt = env && strcmp(env, "simt") == 0;
@@ -596,7 +596,6 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
     v.map_q = static_cast<float*>(dq);
   }
   if (c.kind == JIMM_VIT && c.num_classes > 0) {
-    if (c.num_classes % 4 != 0) { set_last_error("num_classes must be a multiple of 4 (got %d)", c.num_classes); return fail(JIMM_EINVAL); }
     if ((rc = pk.linear("classifier", D, c.num_classes, true, &v.head))) return fail(rc);
   } else if (c.kind == JIMM_CLIP) {
     if ((rc = pk.linear("visual_projection", D, c.t_width, false, &v.head))) return fail(rc);

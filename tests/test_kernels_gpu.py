@@ -86,6 +86,18 @@ def test_gemm_patch_epilogue(lib, mode):
     assert torch.all(got[:, 0] == -7.0)  # CLS rows untouched
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.float16])
+def test_gemm_unaligned_n_scalar_epilogue(lib, mode, out_dtype):
+    """N not a multiple of 4 (e.g. 10 classes): scalar epilogue path, bias + residual."""
+    M, N, K = 37, 10, 128
+    A, B, Ad, Bd = _mk(M, N, K, torch.float16, seed=5)
+    bias = torch.randn(N, device=DEV)
+    ref = Ad @ Bd.T + bias.double()
+    out = gemm(lib, A, B, bias=bias, out_dtype=out_dtype, mode=mode)
+    assert rel_err(out, ref) < (2e-5 if out_dtype == torch.float32 else 2e-3)
+
+
 def test_gemm_strided_and_m_override_tail(lib):
     M, N, K = 130, 264, 200  # N not a multiple of 256/32-chunks-of-8, K tail (200 = 3*64 + 8)
     A, B, Ad, Bd = _mk(M, N, K, torch.float16, seed=4)
@@ -218,8 +230,11 @@ def test_embed_l2_logits(lib):
 def test_bad_arguments_return_errors(lib):
     A = torch.zeros(8, 8, device=DEV).half()
     out = torch.zeros(8, 6, device=DEV)
-    rc = lib.jimm_k_gemm(0, F16, ptr(A), 8, ptr(A), 8, 8, 6, 8, None, 0, None, None, 0, ptr(out), F32, 6, 0, 0, 0, 0, stream())
-    assert rc == -1 and b"multiples of 4" in lib.jimm_last_error()
+    rc = lib.jimm_k_gemm(0, F16, ptr(A), 8, ptr(A), 8, 8, 6, 8, None, 0, None, None, 0, ptr(out), F32, 4, 0, 0, 0, 0, stream())
+    assert rc == -1 and b"ldo" in lib.jimm_last_error()
+    A7 = torch.zeros(8, 7, device=DEV).half()
+    rc = lib.jimm_k_gemm(0, F16, ptr(A7), 7, ptr(A7), 7, 8, 8, 7, None, 0, None, None, 0, ptr(out), F32, 8, 0, 0, 0, 0, stream())
+    assert rc == -1 and b"16-byte aligned" in lib.jimm_last_error()
     x = torch.zeros(2, 6, device=DEV)
     rc = lib.jimm_k_layernorm(ptr(x), 6, 1, 0, None, ptr(x), ptr(x), 1e-6, ptr(x), F32, 6, 2, 6, stream())
     assert rc == -1
