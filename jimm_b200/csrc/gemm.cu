@@ -31,10 +31,14 @@ static constexpr int STAGES = 4;
 static constexpr int A_STAGE_BYTES = BM * 128;
 static constexpr int B_STAGE_BYTES = BN * 128;
 static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-static constexpr int EPI_PITCH = 36;  // floats; conflict-free for 128-bit accesses
-static constexpr int EPI_STAGE_BYTES = 4 * 32 * EPI_PITCH * 4;
+static constexpr int EPI_PITCH = 36;  // floats; conflict-free for 128-bit accesses (modes 0/1 staging)
+static constexpr int EPI_WARPS = 8;   // warps 4..11: lane quarter = warp % 4, column half = (warp - 4) / 4
+static constexpr int EPI_BUF_BYTES = 32 * 128;                       // one 32-row x 128-byte swizzled TMA-store box per warp
+static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;    // 32 KB (modes 0/1 use 4 x 4608 B of it)
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 256 + 1024;
-static constexpr int NUM_THREADS = 256;
+static constexpr int NUM_THREADS = 384;
+static_assert(4 * 32 * EPI_PITCH * 4 <= EPI_STAGE_BYTES, "staging region too small");
+static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 static constexpr uint32_t TMEM_COLS = 512;
 
 struct EpiDev {
@@ -103,7 +107,8 @@ struct Traits<float> {
 
 template <typename T>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const EpiDev epi, int K) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const EpiDev epi, int K) {
   constexpr int BK = 128 / sizeof(T);  // one 128-byte swizzle atom along K per stage
   constexpr int UK = 32 / sizeof(T);   // UMMA K (16 for 16-bit, 8 for tf32)
   constexpr uint32_t IDESC = make_idesc(Traits<T>::FMT, BM, BN);
@@ -130,6 +135,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (epi.mode == 2) tma_prefetch_desc(&map_c);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -138,7 +144,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 4);
+      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -195,8 +201,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
+    const int q = warp_idx & 3;          // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int half = (warp_idx - 4) >> 2; // column half of the 256-wide accumulator this warp drains (mode 2)
     float* st = epi_stage + q * 32 * EPI_PITCH;
+    uint8_t* tbuf = reinterpret_cast<uint8_t*>(epi_stage) + (warp_idx - 4) * EPI_BUF_BYTES;
+    const uint32_t tbuf_u32 = smem_u32(tbuf);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -205,7 +214,73 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tcgen05_fence_after();
       const int row_base = m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if (row_base < M) {
+      if (epi.mode == 2) {
+        // ---- TMA epilogue: thread = row; 32 fp32 (or 64 16-bit) columns -> one swizzled 32 x 128 B box in smem ->
+        //      cp.async.bulk.tensor store (or cp.reduce ... .add for the fp32 residual stream).  Bounds are clipped by TMA.
+        if (row_base < M) {
+          const bool out16 = (epi.out_type == DT_F16 || epi.out_type == DT_BF16);
+          const int cols_per_box = out16 ? 64 : 32;
+          const int c_begin = half * (BN / 2);
+          uint32_t r[32], r2[32];
+          int n0 = n_blk * BN + c_begin;
+          if (n0 < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
+          for (int c = c_begin; c < c_begin + BN / 2; c += cols_per_box) {
+            n0 = n_blk * BN + c;
+            if (n0 >= N) break;
+            tmem_ld_wait();
+            if (out16) tmem_ld_32x32b_x32(taddr + c + 32, r2);  // second half of this box (async)
+            // ---- first 32 columns: bias / activation while the next load is in flight ----
+            uint32_t pk[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (epi.bias && n0 + j < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n0 + j));
+              const float v0 = apply_act(__uint_as_float(r[j]) + b4.x, epi.act), v1 = apply_act(__uint_as_float(r[j + 1]) + b4.y, epi.act);
+              const float v2 = apply_act(__uint_as_float(r[j + 2]) + b4.z, epi.act), v3 = apply_act(__uint_as_float(r[j + 3]) + b4.w, epi.act);
+              if (out16) {
+                pk[j >> 1] = pack2(v0, v1, epi.out_type);
+                pk[(j >> 1) + 1] = pack2(v2, v3, epi.out_type);
+              } else if (epi.out_type == DT_TF32) {
+                pk[j] = __float_as_uint(round_tf32(v0)); pk[j + 1] = __float_as_uint(round_tf32(v1));
+                pk[j + 2] = __float_as_uint(round_tf32(v2)); pk[j + 3] = __float_as_uint(round_tf32(v3));
+              } else {
+                pk[j] = __float_as_uint(v0); pk[j + 1] = __float_as_uint(v1); pk[j + 2] = __float_as_uint(v2); pk[j + 3] = __float_as_uint(v3);
+              }
+            }
+            if (out16) {
+              tmem_ld_wait();
+              const int n1 = n0 + 32;
+              const int cn = c + 64;
+              if (cn < c_begin + BN / 2 && n_blk * BN + cn < N) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch next box
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (epi.bias && n1 + j < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n1 + j));
+                const float v0 = apply_act(__uint_as_float(r2[j]) + b4.x, epi.act), v1 = apply_act(__uint_as_float(r2[j + 1]) + b4.y, epi.act);
+                const float v2 = apply_act(__uint_as_float(r2[j + 2]) + b4.z, epi.act), v3 = apply_act(__uint_as_float(r2[j + 3]) + b4.w, epi.act);
+                pk[16 + (j >> 1)] = pack2(v0, v1, epi.out_type);
+                pk[16 + (j >> 1) + 1] = pack2(v2, v3, epi.out_type);
+              }
+            } else {
+              const int cn = c + 32;
+              if (cn < c_begin + BN / 2 && n_blk * BN + cn < N) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch next box
+            }
+            // ---- stage + TMA store ----
+            if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of smem
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (epi.residual) tma_reduce_add_2d(&map_c, tbuf_u32, n0, row_base);
+              else tma_store_2d(&map_c, tbuf_u32, n0, row_base);
+              tma_store_commit();
+            }
+          }
+        }
+      } else if (half == 0 && row_base < M) {
         for (int c = 0; c < BN / 32; ++c) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= N) break;
@@ -307,6 +382,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   }
 
+  if (warp_idx >= 4 && lane == 0 && epi.mode == 2) tma_store_wait_all();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -423,6 +499,18 @@ int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void
   if (int rc = make_map(&plan->map_a, dtype, A, M, K, lda, BM)) return rc;
   if (int rc = make_map(&plan->map_b, dtype, B, N, K, ldb, BN)) return rc;
   plan->M = M; plan->N = N; plan->K = K; plan->dtype = dtype; plan->epi = epi;
+  memset(&plan->map_c, 0, sizeof(plan->map_c));
+  if (plan->epi.mode == 2) {
+    const size_t es = dtype_size(epi.out_type);
+    const bool ok = epi.rowadd == nullptr && epi.rows_in == 0 && (epi.residual == nullptr || (epi.residual == epi.out && epi.ldr == epi.ldo && epi.out_type == DT_F32)) &&
+                    (static_cast<size_t>(epi.ldo) * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 15) == 0 &&
+                    (epi.bias == nullptr || ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0 && N % 4 == 0));
+    if (ok) {
+      if (int rc = make_map(&plan->map_c, epi.out_type, epi.out, M, N, epi.ldo, 32)) return rc;
+    } else {
+      plan->epi.mode = 0;
+    }
+  }
   return 0;
 }
 
@@ -445,7 +533,7 @@ static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
   }
   const int tiles = ((M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_tcgen05_kernel<T><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, to_dev(p->epi, M, p->N), p->K);
+  gemm_tcgen05_kernel<T><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, to_dev(p->epi, M, p->N), p->K);
   JIMM_LAUNCH_CHECK();
   return 0;
 }

@@ -30,11 +30,14 @@ struct GemmEpilogue {
   int out_type = DT_F32;
   int ldo = 0;                                   // output row stride (elements)
   int rows_in = 0, rows_out = 0, row_off = 0;    // out_row = (r / rows_in) * rows_out + r % rows_in + row_off (rows_in == 0: identity)
-  int mode = 0;                                  // 0: smem-staged, coalesced stores; 1: direct row-per-thread stores
+  // 2: TMA epilogue (swizzled smem box -> cp.async.bulk.tensor store, cp.reduce .add for the fp32 residual stream; needs
+  //    no rowadd / row remap and residual == out) -- falls back to 0 when not applicable;
+  // 0: smem-staged, coalesced LSU stores; 1: direct row-per-thread LSU stores
+  int mode = 2;
 };
 
 struct GemmPlan {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_c;  // map_c: output (mode 2 only)
   int M = 0, N = 0, K = 0;
   int dtype = DT_F16;  // operand type: DT_F16 / DT_BF16 / DT_F32 (tf32 MMA)
   GemmEpilogue epi;

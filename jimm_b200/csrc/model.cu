@@ -175,8 +175,8 @@ struct jimm_model {
   size_t prof_used = 0;
   double prof_flops = 0.0;
   long long prof_launches = 0;
-  int epi_mode_16 = 1;  // epilogue store mode for 16-bit no-residual outputs
-  int epi_mode_res = 0; // epilogue store mode for fp32 residual outputs
+  int epi_mode_16 = 2;  // epilogue mode for 16-bit no-residual outputs (2 = TMA store)
+  int epi_mode_res = 2; // epilogue mode for fp32 residual outputs (2 = TMA reduce-add into the residual stream)
   bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
 };
 
@@ -358,7 +358,7 @@ static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax) {
     JIMM_TRY(gemm_plan_init(&b.p_out, m->cdt, ws.h, c.D, b.out.w, c.D, Tmax, c.D, c.D, epi_residual(b.out, ws.x, c.D, m->epi_mode_res)));
     // FC1: h x W1^T + b1 -> act -> mid [T,M]
     JIMM_TRY(gemm_plan_init(&b.p_fc1, m->cdt, ws.h, c.D, b.fc1.w, c.D, Tmax, c.M, c.D,
-                            epi_plain(b.fc1, act, ws.big, m->cdt, c.M, m->cdt == DT_TF32 ? 0 : m->epi_mode_16)));
+                            epi_plain(b.fc1, act, ws.big, m->cdt, c.M, m->epi_mode_16)));
     // FC2: mid x W2^T + b2 + x -> x
     JIMM_TRY(gemm_plan_init(&b.p_fc2, m->cdt, ws.big, c.M, b.fc2.w, c.M, Tmax, c.D, c.M, epi_residual(b.fc2, ws.x, c.D, m->epi_mode_res)));
   }
@@ -504,8 +504,8 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   m->adt = cfg->compute_dtype == JIMM_BF16 ? DT_BF16 : DT_F16;
   const char* env = getenv("JIMM_GEMM_IMPL");
   m->simt = env && strcmp(env, "simt") == 0;
-  if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env) ? 1 : 0;
-  if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env) ? 1 : 0;
+  if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env);
+  if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env);
   *out = m;
   return 0;
 }

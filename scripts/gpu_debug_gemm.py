@@ -51,18 +51,30 @@ for dtype in (torch.float16, torch.bfloat16, torch.float32):
 print("WORST", worst)
 
 # quick perf probe of the big shapes (CUDA events, 10 reps)
-for (M, N, K) in ((50432, 2304, 768), (50432, 3072, 768), (50432, 768, 3072), (50432, 768, 768)):
+def perf(M, N, K, mode, residual):
     A = torch.randn(M, K, device="cuda").half()
     B = torch.randn(N, K, device="cuda").half()
-    for mode in (0, 1):
+    bias = torch.randn(N, device="cuda")
+    if residual:
+        out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+        kw = dict(residual=out)
+    else:
         out = torch.empty(M, N, device="cuda", dtype=torch.float16)
-        for _ in range(3):
-            gemm(lib, A, B, mode=mode, out=out)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(10):
-            gemm(lib, A, B, mode=mode, out=out)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 10
-        print(f"perf M={M} N={N} K={K} f16 out f16 mode={mode}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+        kw = dict(out=out)
+    for _ in range(3):
+        gemm(lib, A, B, bias=bias, mode=mode, **kw)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        gemm(lib, A, B, bias=bias, mode=mode, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"perf M={M} N={N} K={K} {'f32 residual' if residual else 'f16 out'} mode={mode}: {ms:.3f} ms  {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+
+
+modes = [int(x) for x in os.environ.get("MODES", "0,1,2").split(",")]
+for (M, N, K, res) in ((50432, 2304, 768, False), (50432, 3072, 768, False), (50432, 768, 3072, True), (50432, 768, 768, True),
+                       (73728, 4096, 1024, False), (73728, 1024, 4096, True)):
+    for mode in modes:
+        perf(M, N, K, mode, res)

@@ -34,7 +34,7 @@ def _mk(M, N, K, dtype, seed=0):
 def test_gemm_plain(lib, dtype, M, N, K):
     A, B, Ad, Bd = _mk(M, N, K, dtype)
     ref = Ad @ Bd.T
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         out = gemm(lib, A, B, mode=mode)
         assert rel_err(out, ref) < 2e-5, (mode, rel_err(out, ref))
     simt = gemm(lib, A, B, impl=1)
@@ -43,7 +43,7 @@ def test_gemm_plain(lib, dtype, M, N, K):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("act", [0, 1, 2])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_bias_act_16bit_out(lib, dtype, act, mode):
     M, N, K = 777, 1536, 512
     A, B, Ad, Bd = _mk(M, N, K, dtype, seed=1)
@@ -59,7 +59,7 @@ def test_gemm_bias_act_16bit_out(lib, dtype, act, mode):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_residual_inplace(lib, dtype, mode):
     M, N, K = 650, 768, 256
     A, B, Ad, Bd = _mk(M, N, K, dtype, seed=2)
@@ -71,7 +71,7 @@ def test_gemm_residual_inplace(lib, dtype, mode):
     assert rel_err(out, ref) < 2e-5
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_gemm_patch_epilogue(lib, mode):
     """Row remap + position-embedding add used by the patch-embed GEMM (common/vit.py:231-236)."""
     Bn, n, S, D, K = 3, 16, 17, 128, 192
@@ -86,7 +86,7 @@ def test_gemm_patch_epilogue(lib, mode):
     assert torch.all(got[:, 0] == -7.0)  # CLS rows untouched
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.float16])
 def test_gemm_unaligned_n_scalar_epilogue(lib, mode, out_dtype):
     """N not a multiple of 4 (e.g. 10 classes): scalar epilogue path, bias + residual."""
@@ -102,7 +102,7 @@ def test_gemm_strided_and_m_override_tail(lib):
     M, N, K = 130, 264, 200  # N not a multiple of 256/32-chunks-of-8, K tail (200 = 3*64 + 8)
     A, B, Ad, Bd = _mk(M, N, K, torch.float16, seed=4)
     ref = Ad @ Bd.T
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         assert rel_err(gemm(lib, A, B, mode=mode), ref) < 2e-5
     big = torch.randn(M, 3 * K, device=DEV).half()
     Av = big[:, K:2 * K]  # row stride 3K
