@@ -2,13 +2,23 @@
 //
 //   C[M,N] = epi( A[M,K] . B[N,K]^T ),  A/B K-major fp16 | bf16 | fp32(tf32), fp32 accumulate in TMEM.
 //
-// CTA = 256 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule.
-//   warp 0   : TMA producer (one lane): 4-stage smem ring of {A 128x128B, B 256x128B} tiles, SWIZZLE_128B
-//   warp 1   : MMA issuer  (one lane): tcgen05.mma.cta_group::1 128x256xUMMA_K, accumulators double-buffered
-//              in TMEM (2 x 256 columns), tcgen05.commit releases smem stages / publishes accumulators
-//   warp 2   : TMEM allocator (512 columns)
-//   warps 4-7: epilogue: tcgen05.ld 32x32b.x32 -> bias / GELU / QuickGELU / pos-emb / fp32 residual -> global
+// CTA = 384 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tile schedule (n fastest).
+//   warp 0    : TMA producer (one lane): 4-stage smem ring of {A 128x128B, B 256x128B} tiles, SWIZZLE_128B
+//   warp 1    : MMA issuer  (one lane): tcgen05.mma.cta_group::1 128x256xUMMA_K, accumulators double-buffered
+//               in TMEM (2 x 256 columns), tcgen05.commit releases smem stages / publishes accumulators
+//   warp 2    : TMEM allocator (512 columns)
+//   warps 4-11: epilogue.  warp % 4 = TMEM lane quarter, (warp-4)/4 = column half of the accumulator.
 // Three mbarrier pipelines: smem full/empty (TMA<->MMA), TMEM full/empty (MMA<->epilogue).
+//
+// Epilogues are compile-time specialised (the first version branched at run time on dtype / activation inside 32-way
+// unrolled loops: 174 KB of SASS, instruction-cache misses and exposed bias-load latency -- profiles/r1_a, r1_b):
+//   OUT_H16 / OUT_BF16 / OUT_TF32 / OUT_F32 + ACT {none, tanh-GELU, QuickGELU}: thread = row; tcgen05.ld 32x32b.x32 with
+//       the next chunk prefetched; bias from a per-tile smem copy; pack; 32 x 128 B swizzled box in smem;
+//       cp.async.bulk.tensor store (bounds clipped by the tensor map).
+//   OUT_F32_ADD: the fp32 residual stream x += acc + bias through cp.reduce.async.bulk.tensor .add (done in L2; the SM
+//       never reads the residual).
+//   OUT_GENERIC: everything else (position-embedding row-add + row remap of the patch GEMM, heads with unaligned N,
+//       fp32 stores to caller buffers): LSU stores, run-time flags, 4 epilogue warps.
 //
 // Reference ops served: a1 patch-embed conv-as-GEMM (common/vit.py:153-165,228-236),
 // a4 fused q/k/v projections (common/transformer.py:67-79), a6 out-proj + residual (:130),
@@ -31,15 +41,18 @@ static constexpr int STAGES = 4;
 static constexpr int A_STAGE_BYTES = BM * 128;
 static constexpr int B_STAGE_BYTES = BN * 128;
 static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-static constexpr int EPI_PITCH = 36;  // floats; conflict-free for 128-bit accesses (modes 0/1 staging)
-static constexpr int EPI_WARPS = 8;   // warps 4..11: lane quarter = warp % 4, column half = (warp - 4) / 4
-static constexpr int EPI_BUF_BYTES = 32 * 128;                       // one 32-row x 128-byte swizzled TMA-store box per warp
-static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;    // 32 KB (modes 0/1 use 4 x 4608 B of it)
-static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 256 + 1024;
+static constexpr int EPI_PITCH = 36;  // floats; conflict-free for 128-bit accesses (generic staged path)
+static constexpr int EPI_WARPS = 8;   // warps 4..11
+static constexpr int EPI_BUF_BYTES = 32 * 128;                     // one 32-row x 128-byte swizzled TMA-store box per warp
+static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;  // 32 KB (the generic path uses 4 x 4608 B of it)
+static constexpr int BIAS_BYTES = BN * 4;                          // per-tile bias copy
+static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BIAS_BYTES + 256 + 1024;
 static constexpr int NUM_THREADS = 384;
+static constexpr uint32_t TMEM_COLS = 512;
 static_assert(4 * 32 * EPI_PITCH * 4 <= EPI_STAGE_BYTES, "staging region too small");
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
-static constexpr uint32_t TMEM_COLS = 512;
+
+enum OutKind : int { OUT_GENERIC = 0, OUT_H16 = 1, OUT_BF16 = 2, OUT_TF32 = 3, OUT_F32_ADD = 4, OUT_F32 = 5 };
 
 struct EpiDev {
   const float* bias;
@@ -48,9 +61,16 @@ struct EpiDev {
   void* out;
   int act, ldr, out_type, ldo, rows_in, rows_out, row_off, mode;
   int M, N;
-  int vec;  // 1: N / ldo / ldr are multiples of 4 (8 for 16-bit direct stores) -> vector accesses allowed
+  int debug;
+  int vec;  // 1: N / ldo / ldr multiples of 4 and 16-byte aligned pointers -> vector accesses allowed (generic path)
 };
 
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v) {
+  if constexpr (ACT == ACT_GELU_TANH) return gelu_tanh(v);
+  else if constexpr (ACT == ACT_QUICK_GELU) return quick_gelu(v);
+  else return v;
+}
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_GELU_TANH) return gelu_tanh(v);
   if (act == ACT_QUICK_GELU) return quick_gelu(v);
@@ -105,7 +125,155 @@ struct Traits<float> {
   static constexpr int KIND = 1, FMT = 2;
 };
 
-template <typename T>
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- TMA epilogue for one 128 x 128 half-tile owned by one epilogue warp's lane quarter (thread = row) ------------
+// 16-bit outputs: 64 columns per 32 x 128 B box (two x32 TMEM loads); 32-bit outputs: 32 columns per box.
+template <int OUT, int ACT>
+__device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const EpiDev& epi, uint32_t taddr, const float* sbias, uint8_t* tbuf,
+                                             int lane, int row_base, int n_tile0, int c_begin) {
+  constexpr bool OUT16 = (OUT == OUT_H16 || OUT == OUT_BF16);
+  constexpr int COLS_PER_BOX = OUT16 ? 64 : 32;
+  const int N = epi.N;
+  const uint32_t tbuf_u32 = smem_u32(tbuf);
+  uint32_t r[32], r2[32], pk[32];
+  if (n_tile0 + c_begin < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
+#pragma unroll 1
+  for (int c = c_begin; c < c_begin + BN / 2; c += COLS_PER_BOX) {
+    const int n0 = n_tile0 + c;
+    if (n0 >= N) break;
+    tmem_ld_wait();
+    if constexpr (OUT16) tmem_ld_32x32b_x32(taddr + c + 32, r2);  // second half of this box, in flight during the math below
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + j);
+      const float v0 = act_ct<ACT>(__uint_as_float(r[j]) + b4.x), v1 = act_ct<ACT>(__uint_as_float(r[j + 1]) + b4.y);
+      const float v2 = act_ct<ACT>(__uint_as_float(r[j + 2]) + b4.z), v3 = act_ct<ACT>(__uint_as_float(r[j + 3]) + b4.w);
+      if constexpr (OUT16) {
+        pk[j >> 1] = pack2(v0, v1, OUT == OUT_H16 ? 1 : 2);
+        pk[(j >> 1) + 1] = pack2(v2, v3, OUT == OUT_H16 ? 1 : 2);
+      } else if constexpr (OUT == OUT_TF32) {
+        pk[j] = __float_as_uint(round_tf32(v0)); pk[j + 1] = __float_as_uint(round_tf32(v1));
+        pk[j + 2] = __float_as_uint(round_tf32(v2)); pk[j + 3] = __float_as_uint(round_tf32(v3));
+      } else {
+        pk[j] = __float_as_uint(v0); pk[j + 1] = __float_as_uint(v1); pk[j + 2] = __float_as_uint(v2); pk[j + 3] = __float_as_uint(v3);
+      }
+    }
+    const int cn = c + COLS_PER_BOX;
+    const bool more = (cn < c_begin + BN / 2) && (n_tile0 + cn < N);
+    if constexpr (OUT16) {
+      tmem_ld_wait();
+      if (more) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch the next box
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + 32 + j);
+        const float v0 = act_ct<ACT>(__uint_as_float(r2[j]) + b4.x), v1 = act_ct<ACT>(__uint_as_float(r2[j + 1]) + b4.y);
+        const float v2 = act_ct<ACT>(__uint_as_float(r2[j + 2]) + b4.z), v3 = act_ct<ACT>(__uint_as_float(r2[j + 3]) + b4.w);
+        pk[16 + (j >> 1)] = pack2(v0, v1, OUT == OUT_H16 ? 1 : 2);
+        pk[16 + (j >> 1) + 1] = pack2(v2, v3, OUT == OUT_H16 ? 1 : 2);
+      }
+    } else {
+      if (more) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch the next box
+    }
+    // ---- stage + TMA store ----
+    if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of smem
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (OUT == OUT_F32_ADD) tma_reduce_add_2d(map_c, tbuf_u32, n0, row_base);
+      else tma_store_2d(map_c, tbuf_u32, n0, row_base);
+      tma_store_commit();
+    }
+  }
+}
+
+// ---- generic LSU epilogue (4 warps; run-time flags; modes 0 = staged / 1 = direct) ---------------------------------
+__device__ __noinline__ void epilogue_generic(const EpiDev& epi, uint32_t taddr, float* st, int lane, int row_base, int n_tile0) {
+  const int M = epi.M, N = epi.N;
+  for (int c = 0; c < BN / 32; ++c) {
+    const int n0 = n_tile0 + c * 32;
+    if (n0 >= N) break;
+    uint32_t r[32];
+    tmem_ld_32x32b_x32(taddr + c * 32, r);
+    tmem_ld_wait();
+    if (epi.mode == 1) {
+      // direct: thread owns one row, 32 consecutive columns
+      const int row = row_base + lane;
+      if (row < M) {
+        int out_row, add_row;
+        remap_row(epi, row, out_row, add_row);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = n0 + j;
+          if (col < N) {
+            float v = __uint_as_float(r[j]);
+            if (epi.bias) v += __ldg(epi.bias + col);
+            v = apply_act(v, epi.act);
+            if (epi.rowadd) v += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + col);
+            if (epi.residual) v += epi.residual[static_cast<size_t>(out_row) * epi.ldr + col];
+            store1(epi, out_row, col, v);
+          }
+        }
+      }
+    } else {
+      // staged: transpose through smem so every global access is a full 128-byte line
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(st + lane * EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      __syncwarp();
+      const int cq = (lane & 7) * 4;
+      const int col = n0 + cq;
+      const bool col_ok = epi.vec && (col + 3 < N);
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (epi.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+#pragma unroll 2
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + (lane >> 3);
+        const int row = row_base + rr;
+        float4 v = *reinterpret_cast<const float4*>(st + rr * EPI_PITCH + cq);
+        if (row < M) {
+          int out_row, add_row;
+          remap_row(epi, row, out_row, add_row);
+          if (col_ok) {
+            v.x = apply_act(v.x + b4.x, epi.act);
+            v.y = apply_act(v.y + b4.y, epi.act);
+            v.z = apply_act(v.z + b4.z, epi.act);
+            v.w = apply_act(v.w + b4.w, epi.act);
+            if (epi.rowadd) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(epi.rowadd + static_cast<size_t>(add_row) * N + col));
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            if (epi.residual) {
+              const float4 a = *reinterpret_cast<const float4*>(epi.residual + static_cast<size_t>(out_row) * epi.ldr + col);
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            store4(epi, out_row, col, v);
+          } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4; ++j) {
+              const int cc = col + j;
+              if (cc < N) {
+                float x = vv[j];
+                if (epi.bias) x += __ldg(epi.bias + cc);
+                x = apply_act(x, epi.act);
+                if (epi.rowadd) x += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + cc);
+                if (epi.residual) x += epi.residual[static_cast<size_t>(out_row) * epi.ldr + cc];
+                store1(epi, out_row, cc, x);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <typename T, int OUT, int ACT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const EpiDev epi, int K) {
@@ -117,12 +285,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
-  uint64_t* full_bar = bars;                   // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * STAGES; // [2]
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;// [2]
+  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES + BIAS_BYTES);
+  uint64_t* full_bar = bars;                    // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
+  uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
@@ -131,11 +300,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
+  const bool dbg_no_epi = (epi.debug & 1) != 0, dbg_no_load = (epi.debug & 2) != 0;  // bring-up probes (JIMM_GEMM_DEBUG)
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    if (epi.mode == 2) tma_prefetch_desc(&map_c);
+    if constexpr (OUT != OUT_GENERIC) tma_prefetch_desc(&map_c);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -163,9 +333,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-          tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (dbg_no_load) {
+            mbar_arrive(&full_bar[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -201,188 +375,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp_idx >= 4) {
     // ===================== epilogue =====================
-    const int q = warp_idx & 3;          // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
-    const int half = (warp_idx - 4) >> 2; // column half of the 256-wide accumulator this warp drains (mode 2)
-    float* st = epi_stage + q * 32 * EPI_PITCH;
-    uint8_t* tbuf = reinterpret_cast<uint8_t*>(epi_stage) + (warp_idx - 4) * EPI_BUF_BYTES;
-    const uint32_t tbuf_u32 = smem_u32(tbuf);
+    const int q = warp_idx & 3;            // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int half = (warp_idx - 4) >> 2;  // column half of the 256-wide accumulator this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int row_base = m_blk * BM + q * 32;
+      if constexpr (OUT != OUT_GENERIC) {
+        // per-tile bias copy (one coalesced 128-bit load per lane of two warps), overlapped with the wait for the MMAs
+        named_bar_sync(1, EPI_WARPS * 32);  // every epilogue warp is done with the previous tile's bias
+        if (q == 0) {
+          const int col = n_blk * BN + half * (BN / 2) + lane * 4;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (epi.bias && col < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
+          *reinterpret_cast<float4*>(sbias + half * (BN / 2) + lane * 4) = b4;
+        }
+        named_bar_sync(1, EPI_WARPS * 32);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
-      const int row_base = m_blk * BM + q * 32;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-      if (epi.mode == 2) {
-        // ---- TMA epilogue: thread = row; 32 fp32 (or 64 16-bit) columns -> one swizzled 32 x 128 B box in smem ->
-        //      cp.async.bulk.tensor store (or cp.reduce ... .add for the fp32 residual stream).  Bounds are clipped by TMA.
-        if (row_base < M) {
-          const bool out16 = (epi.out_type == DT_F16 || epi.out_type == DT_BF16);
-          const int cols_per_box = out16 ? 64 : 32;
-          const int c_begin = half * (BN / 2);
-          uint32_t r[32], r2[32];
-          int n0 = n_blk * BN + c_begin;
-          if (n0 < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
-          for (int c = c_begin; c < c_begin + BN / 2; c += cols_per_box) {
-            n0 = n_blk * BN + c;
-            if (n0 >= N) break;
-            tmem_ld_wait();
-            if (out16) tmem_ld_32x32b_x32(taddr + c + 32, r2);  // second half of this box (async)
-            // ---- first 32 columns: bias / activation while the next load is in flight ----
-            uint32_t pk[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (epi.bias && n0 + j < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n0 + j));
-              const float v0 = apply_act(__uint_as_float(r[j]) + b4.x, epi.act), v1 = apply_act(__uint_as_float(r[j + 1]) + b4.y, epi.act);
-              const float v2 = apply_act(__uint_as_float(r[j + 2]) + b4.z, epi.act), v3 = apply_act(__uint_as_float(r[j + 3]) + b4.w, epi.act);
-              if (out16) {
-                pk[j >> 1] = pack2(v0, v1, epi.out_type);
-                pk[(j >> 1) + 1] = pack2(v2, v3, epi.out_type);
-              } else if (epi.out_type == DT_TF32) {
-                pk[j] = __float_as_uint(round_tf32(v0)); pk[j + 1] = __float_as_uint(round_tf32(v1));
-                pk[j + 2] = __float_as_uint(round_tf32(v2)); pk[j + 3] = __float_as_uint(round_tf32(v3));
-              } else {
-                pk[j] = __float_as_uint(v0); pk[j + 1] = __float_as_uint(v1); pk[j + 2] = __float_as_uint(v2); pk[j + 3] = __float_as_uint(v3);
-              }
-            }
-            if (out16) {
-              tmem_ld_wait();
-              const int n1 = n0 + 32;
-              const int cn = c + 64;
-              if (cn < c_begin + BN / 2 && n_blk * BN + cn < N) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch next box
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (epi.bias && n1 + j < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n1 + j));
-                const float v0 = apply_act(__uint_as_float(r2[j]) + b4.x, epi.act), v1 = apply_act(__uint_as_float(r2[j + 1]) + b4.y, epi.act);
-                const float v2 = apply_act(__uint_as_float(r2[j + 2]) + b4.z, epi.act), v3 = apply_act(__uint_as_float(r2[j + 3]) + b4.w, epi.act);
-                pk[16 + (j >> 1)] = pack2(v0, v1, epi.out_type);
-                pk[16 + (j >> 1) + 1] = pack2(v2, v3, epi.out_type);
-              }
-            } else {
-              const int cn = c + 32;
-              if (cn < c_begin + BN / 2 && n_blk * BN + cn < N) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch next box
-            }
-            // ---- stage + TMA store ----
-            if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of smem
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(tbuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (epi.residual) tma_reduce_add_2d(&map_c, tbuf_u32, n0, row_base);
-              else tma_store_2d(&map_c, tbuf_u32, n0, row_base);
-              tma_store_commit();
-            }
-          }
-        }
-      } else if (half == 0 && row_base < M) {
-        for (int c = 0; c < BN / 32; ++c) {
-          const int n0 = n_blk * BN + c * 32;
-          if (n0 >= N) break;
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
-          tmem_ld_wait();
-          if (epi.mode == 1) {
-            // ---- direct: thread owns one row, 32 consecutive columns ----
-            const int row = row_base + lane;
-            if (row < M) {
-              int out_row, add_row;
-              remap_row(epi, row, out_row, add_row);
-              const bool full = (n0 + 32 <= N);
-              if (full && epi.vec && (epi.out_type == DT_F16 || epi.out_type == DT_BF16) && epi.rowadd == nullptr && epi.residual == nullptr) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                  float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-                  if (epi.bias) { v0 += __ldg(epi.bias + n0 + j); v1 += __ldg(epi.bias + n0 + j + 1); }
-                  v0 = apply_act(v0, epi.act);
-                  v1 = apply_act(v1, epi.act);
-                  pk[j >> 1] = pack2(v0, v1, epi.out_type);
-                }
-                uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(epi.out) + static_cast<size_t>(out_row) * epi.ldo + n0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                  const int col = n0 + j;
-                  if (col < N) {
-                    float v = __uint_as_float(r[j]);
-                    if (epi.bias) v += __ldg(epi.bias + col);
-                    v = apply_act(v, epi.act);
-                    if (epi.rowadd) v += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + col);
-                    if (epi.residual) v += epi.residual[static_cast<size_t>(out_row) * epi.ldr + col];
-                    store1(epi, out_row, col, v);
-                  }
-                }
-              }
-            }
-          } else {
-            // ---- staged: transpose through smem so every global access is a full 128-byte line ----
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<uint4*>(st + lane * EPI_PITCH + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-            __syncwarp();
-            const int cq = (lane & 7) * 4;
-            const int col = n0 + cq;
-            const bool col_ok = epi.vec && (col + 3 < N);
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (epi.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + (lane >> 3);
-              const int row = row_base + rr;
-              float4 v = *reinterpret_cast<const float4*>(st + rr * EPI_PITCH + cq);
-              if (row < M) {
-                int out_row, add_row;
-                remap_row(epi, row, out_row, add_row);
-                if (col_ok) {
-                  v.x = apply_act(v.x + b4.x, epi.act);
-                  v.y = apply_act(v.y + b4.y, epi.act);
-                  v.z = apply_act(v.z + b4.z, epi.act);
-                  v.w = apply_act(v.w + b4.w, epi.act);
-                  if (epi.rowadd) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(epi.rowadd + static_cast<size_t>(add_row) * N + col));
-                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                  }
-                  if (epi.residual) {
-                    const float4 a = *reinterpret_cast<const float4*>(epi.residual + static_cast<size_t>(out_row) * epi.ldr + col);
-                    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                  }
-                  store4(epi, out_row, col, v);
-                } else {
-                  const float vv[4] = {v.x, v.y, v.z, v.w};
-                  for (int j = 0; j < 4; ++j) {
-                    const int cc = col + j;
-                    if (cc < N) {
-                      float x = vv[j];
-                      if (epi.bias) x += __ldg(epi.bias + cc);
-                      x = apply_act(x, epi.act);
-                      if (epi.rowadd) x += __ldg(epi.rowadd + static_cast<size_t>(add_row) * N + cc);
-                      if (epi.residual) x += epi.residual[static_cast<size_t>(out_row) * epi.ldr + cc];
-                      store1(epi, out_row, cc, x);
-                    }
-                  }
-                }
-              }
-            }
-            __syncwarp();
-          }
-        }
+      if (dbg_no_epi) {
+      } else if constexpr (OUT != OUT_GENERIC) {
+        if (row_base < M)
+          epilogue_tma<OUT, ACT>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUF_BYTES, lane, row_base, n_blk * BN, half * (BN / 2));
+      } else {
+        if (half == 0 && row_base < M)
+          epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_blk * BN);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if constexpr (OUT != OUT_GENERIC) {
+      if (lane == 0) tma_store_wait_all();
+    }
   }
 
-  if (warp_idx >= 4 && lane == 0 && epi.mode == 2) tma_store_wait_all();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -482,10 +513,9 @@ static int check_epi(const GemmEpilogue& e, int N) {
   if (e.ldo < N) { set_last_error("gemm: ldo (%d) < N (%d)", e.ldo, N); return -1; }
   return 0;
 }
-// vector accesses need aligned rows; otherwise the epilogue takes its scalar path (tiny head GEMMs such as N = 10 classes)
+// vector accesses need aligned rows; otherwise the generic epilogue takes its scalar path (tiny head GEMMs, N = 10 classes)
 static int epi_vec_ok(const GemmEpilogue& e, int N) {
-  const int a = (e.mode == 1 && (e.out_type == DT_F16 || e.out_type == DT_BF16)) ? 8 : 4;
-  if (N % 4 != 0 || e.ldo % a != 0) return 0;
+  if (N % 4 != 0 || e.ldo % 4 != 0) return 0;
   if (e.residual && e.ldr % 4 != 0) return 0;
   if ((reinterpret_cast<uintptr_t>(e.out) & 15) || (reinterpret_cast<uintptr_t>(e.bias) & 15) ||
       (reinterpret_cast<uintptr_t>(e.residual) & 15) || (reinterpret_cast<uintptr_t>(e.rowadd) & 15)) return 0;
@@ -502,9 +532,11 @@ int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void
   memset(&plan->map_c, 0, sizeof(plan->map_c));
   if (plan->epi.mode == 2) {
     const size_t es = dtype_size(epi.out_type);
-    const bool ok = epi.rowadd == nullptr && epi.rows_in == 0 && (epi.residual == nullptr || (epi.residual == epi.out && epi.ldr == epi.ldo && epi.out_type == DT_F32)) &&
+    const bool ok = epi.rowadd == nullptr && epi.rows_in == 0 &&
+                    (epi.residual == nullptr || (epi.residual == epi.out && epi.ldr == epi.ldo && epi.out_type == DT_F32)) &&
                     (static_cast<size_t>(epi.ldo) * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 15) == 0 &&
-                    (epi.bias == nullptr || ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0 && N % 4 == 0));
+                    (epi.bias == nullptr || ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0 && N % 4 == 0)) &&
+                    !(epi.residual && epi.act != ACT_NONE);
     if (ok) {
       if (int rc = make_map(&plan->map_c, epi.out_type, epi.out, M, N, epi.ldo, 32)) return rc;
     } else {
@@ -521,21 +553,46 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.rows_in = e.rows_in; d.rows_out = e.rows_out; d.row_off = e.row_off; d.mode = e.mode;
   d.M = M; d.N = N;
   d.vec = epi_vec_ok(e, N);
+  static int dbg = -1;
+  if (dbg < 0) { const char* env = getenv("JIMM_GEMM_DEBUG"); dbg = env ? atoi(env) : 0; }
+  d.debug = dbg;
   return d;
 }
 
-template <typename T>
-static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
+template <typename T, int OUT, int ACT>
+static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_tcgen05_kernel<T><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, to_dev(p->epi, M, p->N), p->K);
+  gemm_tcgen05_kernel<T, OUT, ACT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, to_dev(p->epi, M, p->N), p->K);
   JIMM_LAUNCH_CHECK();
   return 0;
+}
+
+template <typename T, int OUT>
+static int launch_act(const GemmPlan* p, int M, cudaStream_t stream) {
+  switch (p->epi.act) {
+    case ACT_GELU_TANH: return launch_one<T, OUT, ACT_GELU_TANH>(p, M, stream);
+    case ACT_QUICK_GELU: return launch_one<T, OUT, ACT_QUICK_GELU>(p, M, stream);
+    default: return launch_one<T, OUT, ACT_NONE>(p, M, stream);
+  }
+}
+
+template <typename T>
+static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
+  const GemmEpilogue& e = p->epi;
+  if (e.mode != 2) return launch_one<T, OUT_GENERIC, ACT_NONE>(p, M, stream);
+  if (e.residual) return launch_one<T, OUT_F32_ADD, ACT_NONE>(p, M, stream);
+  switch (e.out_type) {
+    case DT_F16: return launch_act<T, OUT_H16>(p, M, stream);
+    case DT_BF16: return launch_act<T, OUT_BF16>(p, M, stream);
+    case DT_TF32: return launch_act<T, OUT_TF32>(p, M, stream);
+    default: return launch_act<T, OUT_F32>(p, M, stream);
+  }
 }
 
 int gemm_plan_run(const GemmPlan* p, int M_override, cudaStream_t stream) {

@@ -44,11 +44,12 @@ def run(M, N, K, dtype, mode):
 
 
 worst = 0.0
-for dtype in (torch.float16, torch.bfloat16, torch.float32):
-    for (M, N, K) in ((128, 256, 64), (128, 256, 256), (256, 512, 768), (1000, 1000, 512)):
-        for mode in (0, 1):
-            worst = max(worst, run(M, N, K, dtype, mode))
-print("WORST", worst)
+if not os.environ.get("PERF_ONLY"):
+    for dtype in (torch.float16, torch.bfloat16, torch.float32):
+        for (M, N, K) in ((128, 256, 64), (128, 256, 256), (256, 512, 768), (1000, 1000, 512)):
+            for mode in (0, 1, 2):
+                worst = max(worst, run(M, N, K, dtype, mode))
+    print("WORST", worst)
 
 # quick perf probe of the big shapes (CUDA events, 10 reps)
 def perf(M, N, K, mode, residual):

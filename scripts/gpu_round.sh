@@ -13,6 +13,8 @@ for s in $STAGES; do
     smoke)   timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     bench)   timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?" ;;
+    probe)   for d in 0 1 2 3; do echo "== JIMM_GEMM_DEBUG=$d"; JIMM_GEMM_DEBUG=$d PERF_ONLY=1 MODES=2 timeout 120 python scripts/gpu_debug_gemm.py 2>&1 | grep perf; done > gpurun_out/probe.log 2>&1; echo "probe rc=$?" ;;
+    ncu_src) timeout 600 ncu --set full --section SourceCounters --clock-control none --import-source on -k regex:gemm_tcgen05 -s 3 -c 2 -o gpurun_out/prof_gemm_src -f env PERF_ONLY=1 MODES=2 python scripts/gpu_debug_gemm.py > gpurun_out/ncu_src.log 2>&1; echo "ncu_src rc=$?" ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_list.log 2>&1; echo "ncu_list rc=$?" ;;
     ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 20 -c 4 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu_full rc=$?" ;;
   esac
@@ -22,3 +24,4 @@ tail -n 15 gpurun_out/kernels.log 2>/dev/null
 tail -n 15 gpurun_out/parity.log 2>/dev/null
 tail -n 5 gpurun_out/smoke.log 2>/dev/null
 tail -n 3 gpurun_out/bench.log gpurun_out/bench.err 2>/dev/null
+cat gpurun_out/probe.log 2>/dev/null
