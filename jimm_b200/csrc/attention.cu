@@ -8,6 +8,9 @@
 // of this kernel is listed as the next optimisation in DESIGN.md.
 //
 // map_attention_kernel: MAP-head pooling attention with a single precomputed probe query (common/vit.py:96-97).
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -271,6 +274,11 @@ static int attn_launch(const void* qkv, void* out, int B, int S, int H, int caus
 
 int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
   if (B <= 0 || S <= 0) return 0;
+  const char* env = getenv("JIMM_ATTN_IMPL");  // "flash" forces the mma.sync flash kernel (A/B comparison, bisection)
+  if (!(env && strcmp(env, "flash") == 0)) {
+    const int rc = attention_tc_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
+    if (rc <= 0) return rc;
+  }
   if (B > 65535 || H > 65535) { set_last_error("attention: grid too large (B=%d H=%d)", B, H); return -1; }
   if (io_type == DT_F16 && out_type == DT_F16) return attn_launch<__half, __half>(qkv, out, B, S, H, causal, stream);
   if (io_type == DT_F16 && out_type == DT_F32) return attn_launch<__half, float>(qkv, out, B, S, H, causal, stream);

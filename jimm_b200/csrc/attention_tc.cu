@@ -1,0 +1,278 @@
+// tcgen05 softmax attention for sequences of up to 256 tokens, head_dim 64.
+//
+//   o[b*S+s, h*64+d] = softmax_k((q/8) k^T  masked) v            nnx.MultiHeadAttention core, common/transformer.py:130
+//
+// Every jimm tower with S <= 256 lands here (ViT-B/16@224: 197, SigLIP-B/16@256: 256, CLIP-B/32: 50 / 77 causal); longer
+// sequences use the flash kernel in attention.cu.  With S <= 256 a whole score row fits one TMEM accumulator, so there is
+// no online-softmax rescaling: one persistent CTA per SM loops over (sample, head) items:
+//
+//   warp 0   TMA: Q, K, V of the item (three 256 x 128 B boxes of the fused qkv buffer, SWIZZLE_128B), 2-deep ring
+//   warp 1   MMA: S_t = Q_t K^T  (tcgen05.mma SS, M=128, N=ceil16(S), K=64) for the one or two 128-row query tiles t,
+//                 then O_t = P_t V (tcgen05.mma with A = P_t read from TENSOR MEMORY, B = V as an MN-major smem operand)
+//   warp 2   TMEM allocator (512 columns: tile t owns columns [256t, 256t+256): S, overwritten in place by fp16/bf16 P in
+//            the first N/2 columns, O in columns 128..191)
+//   warps 4-11  softmax + output, one group of 4 warps per query tile, thread = query row: pass 1 row max from TMEM,
+//            pass 2 exp2 / row sum / pack / tcgen05.st P, then O * (1/l) -> global after the P V MMA.
+// The kernel is MUFU(exp2)-bound by construction (S^2 exponentials per head vs 4 S^2 64 MACs on the tensor pipe).
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jimm {
+
+static constexpr int ATC_THREADS = 384;
+static constexpr int ATC_TILE_BYTES = 256 * 128;                 // one Q / K / V box
+static constexpr int ATC_BUF_BYTES = 3 * ATC_TILE_BYTES;          // 96 KB per item
+static constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 256 + 1024;
+
+struct AtcParams {
+  int B, S, H, D;
+  int nq;       // query tiles per item (1 or 2)
+  int Nk;       // keys rounded up to 16 (MMA N of S = Q K^T, MMA K of O = P V)
+  float scale_log2;
+  void* out;
+};
+
+template <typename T, typename OutT, bool CAUSAL>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams p) {
+  constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATC_BUF_BYTES);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* s_full = bars + 4;     // [2] per query tile
+  uint64_t* p_ready = bars + 6;    // [2]
+  uint64_t* o_full = bars + 8;     // [2]
+  uint64_t* slot_free = bars + 10; // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_items = p.B * p.H;
+
+  if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&slot_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc(tmem_ptr_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item - b * p.H;
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        uint8_t* base = smem + buf * ATC_BUF_BYTES;
+        mbar_wait(&kv_empty[buf], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[buf], ATC_BUF_BYTES);
+        const int row0 = b * p.S;
+        tma_load_2d(base, &map_qkv, &kv_full[buf], h * 64, row0);
+        tma_load_2d(base + ATC_TILE_BYTES, &map_qkv, &kv_full[buf], p.D + h * 64, row0);
+        tma_load_2d(base + 2 * ATC_TILE_BYTES, &map_qkv, &kv_full[buf], 2 * p.D + h * 64, row0);
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc(FMT, 128, static_cast<uint32_t>(p.Nk), 0);
+      const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1, sp = it & 1;
+        const uint32_t q_addr = smem_u32(smem + buf * ATC_BUF_BYTES);
+        const uint32_t k_addr = q_addr + ATC_TILE_BYTES, v_addr = q_addr + 2 * ATC_TILE_BYTES;
+        mbar_wait(&kv_full[buf], ph);
+        tcgen05_fence_after();
+        for (int t = 0; t < p.nq; ++t) {
+          mbar_wait(&slot_free[t], sp ^ 1);  // the previous item's O of this tile has been read out
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32),
+                       idesc_qk, k > 0 ? 1u : 0u);
+          tcgen05_commit(&s_full[t]);
+        }
+        for (int t = 0; t < p.nq; ++t) {
+          mbar_wait(&p_ready[t], sp);
+          tcgen05_fence_after();
+          for (int kk = 0; kk < p.Nk / 16; ++kk)
+            umma_ts_f16(tmem_base + t * 256 + 128, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
+                        kk > 0 ? 1u : 0u);
+          tcgen05_commit(&o_full[t]);
+        }
+        tcgen05_commit(&kv_empty[buf]);  // every MMA reading this item's smem has retired
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== softmax + output =====================
+    const int q = warp_idx & 3;        // TMEM lane quarter
+    const int t = (warp_idx - 4) >> 2; // query tile
+    if (t < p.nq) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+      const int row = t * 128 + q * 32 + lane;  // query index inside the sample
+      const int S = p.S;
+      int kmax = S;  // number of keys this row attends to
+      if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
+      // warp-uniform upper bound of keys any row of this warp needs (rows >= S are clamped: finite garbage, never stored)
+      const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
+      const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item - b * p.H;
+        const uint32_t sp = it & 1;
+        mbar_wait(&s_full[t], sp);
+        tcgen05_fence_after();
+        // ---- pass 1: row max ----
+        float m = -INFINITY;
+        uint32_t r[32];
+        for (int c = 0; c < n_live; ++c) {
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(r[j]);
+            m = (c * 32 + j < kmax) ? fmaxf(m, v) : m;
+          }
+        }
+        const float moff = m * p.scale_log2;
+        // ---- pass 2: p = exp2(s * scale - max), row sum, P (16-bit) back into TMEM over the consumed S columns ----
+        float l = 0.f;
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t pk[16];
+          if (c < n_live) {
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -moff));
+              float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -moff));
+              p0 = (c * 32 + j < kmax) ? p0 : 0.f;
+              p1 = (c * 32 + j + 1 < kmax) ? p1 : 0.f;
+              l += p0 + p1;
+              pk[j >> 1] = pack2(p0, p1, FMT == 0 ? 1 : 2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          }
+          tmem_st_32x32b_x16(taddr + c * 16, pk);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[t]);
+        // ---- output: O / l ----
+        const float inv = 1.0f / l;
+        mbar_wait(&o_full[t], sp);
+        tcgen05_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32b_x32(taddr + 128, o0);
+        tmem_ld_32x32b_x32(taddr + 160, o1);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slot_free[t]);  // TMEM of this tile may be overwritten by the next item's S
+        if (row < S) {
+          const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64;
+          if constexpr (sizeof(OutT) == 2) {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + off);
+            constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack2(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv, ot),
+                                  pack2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv, ot),
+                                  pack2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv, ot),
+                                  pack2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv, ot));
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[4 + j] = make_uint4(pack2(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv, ot),
+                                      pack2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv, ot),
+                                      pack2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv, ot),
+                                      pack2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv, ot));
+          } else {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off);
+            constexpr bool RT = std::is_same<OutT, tf32_t>::value;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(o0[4 * j]) * inv, __uint_as_float(o0[4 * j + 1]) * inv,
+                                     __uint_as_float(o0[4 * j + 2]) * inv, __uint_as_float(o0[4 * j + 3]) * inv);
+              if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+              dst[j] = v;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 v = make_float4(__uint_as_float(o1[4 * j]) * inv, __uint_as_float(o1[4 * j + 1]) * inv,
+                                     __uint_as_float(o1[4 * j + 2]) * inv, __uint_as_float(o1[4 * j + 3]) * inv);
+              if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+              dst[8 + j] = v;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host ----------------------------------------------------------------------------------------------------------
+int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows);  // gemm.cu
+
+template <typename T, typename OutT>
+static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int H, int causal, cudaStream_t stream) {
+  const int D = H * 64;
+  CUtensorMap map;
+  if (int rc = make_tensor_map_2d(&map, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
+  AtcParams p;
+  p.B = B; p.S = S; p.H = H; p.D = D;
+  p.nq = (S + 127) / 128;
+  p.Nk = ((S + 15) / 16) * 16;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.out = out;
+  const int items = B * H;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  static bool attr_set = false;
+  if (!attr_set) {
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+    attr_set = true;
+  }
+  if (causal) attention_tc_kernel<T, OutT, true><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(map, p);
+  else attention_tc_kernel<T, OutT, false><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(map, p);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
+// Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
+int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+  if (S > 256 || S < 1) return 1;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+  if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_TF32) return atc_launch<__half, tf32_t>(qkv, io_type, out, B, S, H, causal, stream);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return atc_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, B, S, H, causal, stream);
+  if (io_type == DT_BF16 && out_type == DT_F32) return atc_launch<__nv_bfloat16, float>(qkv, io_type, out, B, S, H, causal, stream);
+  return 1;
+}
+
+}  // namespace jimm

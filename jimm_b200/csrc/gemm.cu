@@ -496,6 +496,10 @@ static int make_map(CUtensorMap* map, int dtype, const void* ptr, int rows, int 
   return 0;
 }
 
+int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  return make_map(map, dtype, ptr, rows, cols, ld, box_rows);
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

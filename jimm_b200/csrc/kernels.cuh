@@ -42,6 +42,9 @@ int cast_run(const float* src, void* dst, int out_type, size_t n, cudaStream_t s
 //   o[b*S+s, h*64+d] = softmax_k((q/8) k^T  masked) v ; causal: key <= query.  io_type fp16/bf16; out_type fp16/bf16/fp32
 int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
 
+// tcgen05 variant for S <= 256 (attention_tc.cu); returns 1 when the configuration is not handled (caller falls back).
+int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
+
 // MAP-head attention with a single (input-independent) probe query (common/vit.py:96-97).
 //   q: fp32 [H*64] (already projected + biased), kv: [B*S, 2D] (k | v) io_type, out [B, D] out_type
 int map_attention_run(const float* q, const void* kv, int io_type, void* out, int out_type, int B, int S, int H, cudaStream_t stream);

@@ -7,6 +7,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 for s in $STAGES; do
   case $s in
     debug)   timeout 300 python scripts/gpu_debug_gemm.py > gpurun_out/debug_gemm.log 2>&1; echo "debug rc=$?" ;;
+    attn)    timeout 240 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k attention --timeout 60 > gpurun_out/attn.log 2>&1; echo "attn rc=$?"; tail -n 12 gpurun_out/attn.log ;;
     kernels) timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 300 > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" ;;
     kernels_all) timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu --timeout 300 > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" ;;
     parity)  timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu --timeout 600 > gpurun_out/parity.log 2>&1; echo "parity rc=$?" ;;

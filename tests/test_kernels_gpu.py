@@ -169,6 +169,26 @@ def test_attention(lib, dtype, S, causal):
         assert rel_err(out, ref) < tol, (S, causal, out_dtype, rel_err(out, ref))
 
 
+@pytest.mark.parametrize("S,causal", [(50, 0), (77, 1), (197, 0), (256, 1)])
+def test_attention_flash_kernel_forced(lib, monkeypatch, S, causal):
+    """S <= 256 normally takes the tcgen05 kernel; JIMM_ATTN_IMPL=flash keeps the mma.sync kernel covered there too."""
+    monkeypatch.setenv("JIMM_ATTN_IMPL", "flash")
+    B, H = 2, 3
+    qkv = (torch.randn(B * S, 3 * H * 64, device=DEV) * 1.5).half()
+    out = torch.empty(B * S, H * 64, dtype=torch.float16, device=DEV)
+    check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F16, B, S, H, causal, stream()))
+    assert rel_err(out, _attn_ref(qkv, B, S, H, causal)) < 3e-3
+
+
+def test_attention_many_items_persistent(lib):
+    """More (sample, head) items than SMs: exercises the persistent loop, the 2-deep smem ring and TMEM slot reuse."""
+    B, S, H = 40, 197, 12
+    qkv = (torch.randn(B * S, 3 * H * 64, device=DEV)).half()
+    out = torch.empty(B * S, H * 64, dtype=torch.float16, device=DEV)
+    check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F16, B, S, H, 0, stream()))
+    assert rel_err(out, _attn_ref(qkv, B, S, H, 0)) < 3e-3
+
+
 def test_attention_large_scores_stable(lib):
     B, S, H = 1, 130, 1
     qkv = (torch.randn(B * S, 3 * 64, device=DEV) * 12).half()
