@@ -170,6 +170,10 @@ struct jimm_model {
   float* logit_bias = nullptr;
   Workspace ws;
   CommState comm;
+  cudaStream_t copy_stream = nullptr;            // host path: H2D of chunk i+1 overlaps the forward of chunk i
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -701,6 +705,11 @@ int jimm_model_destroy(jimm_model_t* m) {
   cudaDeviceSynchronize();
   comm_destroy(&m->comm);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+  if (m->copy_stream) {
+    cudaStreamDestroy(m->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_consumed[i]); }
+    cudaEventDestroy(m->ev_start);
+  }
   m->pool.release();
   delete m;
   return 0;
@@ -785,13 +794,40 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host on a dual-tower model"); return JIMM_EINVAL; }
   JIMM_TRY(set_device(m));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!m->copy_stream) {
+    JIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+      JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_consumed[i], cudaEventDisableTiming));
+    }
+    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  }
   const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
   const int od = vision_out_dim(m);
-  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
-    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, static_cast<const uint8_t*>(img_host) + b0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, s));
-    JIMM_TRY(run_vision(m, m->ws.in_img, in_dtype, nb, m->ws.out_dev, s));
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  // Chunked double-buffered pipeline: the staging buffer (max_batch fp32 images) is split into two slots of `chunk` images;
+  // the H2D copy of chunk i+1 runs on the side stream while chunk i is in the tower.
+  int chunk = m->max_batch / 2;
+  static int chunk_cap = -1;
+  if (chunk_cap < 0) { const char* env = getenv("JIMM_HOST_CHUNK"); chunk_cap = (env && atoi(env) > 0) ? atoi(env) : 128; }
+  if (chunk > chunk_cap) chunk = chunk_cap;
+  const bool pipelined = chunk >= 16 && B > chunk;
+  if (!pipelined) chunk = m->max_batch;
+  const size_t slot_bytes = static_cast<size_t>(chunk) * m->vis.img * m->vis.img * m->vis.C * sizeof(float);
+  JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
+  JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+  int ci = 0;
+  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
+    const int nb = B - b0 < chunk ? B - b0 : chunk;
+    const int slot = pipelined ? (ci & 1) : 0;
+    uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + slot * slot_bytes;
+    float* out_d = m->ws.out_dev + static_cast<size_t>(slot) * chunk * od;
+    if (ci >= (pipelined ? 2 : 1)) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + b0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, m->copy_stream));
+    JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
+    JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
+    JIMM_TRY(run_vision(m, dst, in_dtype, nb, out_d, s));
+    JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, out_d, static_cast<size_t>(nb) * od * sizeof(float), cudaMemcpyDeviceToHost, s));
   }
   return 0;
 }
