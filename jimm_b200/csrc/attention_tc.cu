@@ -139,39 +139,62 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         const uint32_t sp = it & 1;
         mbar_wait(&s_full[t], sp);
         tcgen05_fence_after();
-        // ---- pass 1: row max ----
+        // ---- pass 1: row max (next chunk's TMEM load in flight while this one is reduced) ----
         float m = -INFINITY;
-        uint32_t r[32];
-        for (int c = 0; c < n_live; ++c) {
-          tmem_ld_32x32b_x32(taddr + c * 32, r);
+        uint32_t r[32], rn[32];
+        tmem_ld_32x32b_x32(taddr, r);
+        for (int c = 0; c < n_live; c += 2) {
           tmem_ld_wait();
+          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float v = __uint_as_float(r[j]);
             m = (c * 32 + j < kmax) ? fmaxf(m, v) : m;
           }
+          if (c + 1 < n_live) {
+            tmem_ld_wait();
+            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(rn[j]);
+              m = ((c + 1) * 32 + j < kmax) ? fmaxf(m, v) : m;
+            }
+          }
         }
         const float moff = m * p.scale_log2;
         // ---- pass 2: p = exp2(s * scale - max), row sum, P (16-bit) back into TMEM over the consumed S columns ----
+        // P chunk c (16 columns) lands on S columns [16c, 16c+16) which belong to S chunk c/2 <= c: already in registers.
+        // With the one-chunk-ahead prefetch S chunk c+1 is read BEFORE P chunk c is stored, and 16(c)+16 <= 32(c+1), so the
+        // store never clobbers a chunk that has not been loaded yet.
         float l = 0.f;
-        for (int c = 0; c < n_chunks; ++c) {
+        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
           uint32_t pk[16];
-          if (c < n_live) {
-            tmem_ld_32x32b_x32(taddr + c * 32, r);
-            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float p0 = ex2_approx(fmaf(__uint_as_float(r[j]), p.scale_log2, -moff));
-              float p1 = ex2_approx(fmaf(__uint_as_float(r[j + 1]), p.scale_log2, -moff));
-              p0 = (c * 32 + j < kmax) ? p0 : 0.f;
-              p1 = (c * 32 + j + 1 < kmax) ? p1 : 0.f;
-              l += p0 + p1;
-              pk[j >> 1] = pack2(p0, p1, FMT == 0 ? 1 : 2);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) pk[j] = 0u;
+          for (int j = 0; j < 32; j += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2, -moff));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -moff));
+            p0 = (c * 32 + j < kmax) ? p0 : 0.f;
+            p1 = (c * 32 + j + 1 < kmax) ? p1 : 0.f;
+            l += p0 + p1;
+            pk[j >> 1] = pack2(p0, p1, FMT == 0 ? 1 : 2);
           }
+          tmem_st_32x32b_x16(taddr + c * 16, pk);
+        };
+        tmem_ld_32x32b_x32(taddr, r);
+        for (int c = 0; c < n_live; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
+          softmax_chunk(r, c);
+          if (c + 1 < n_live) {
+            tmem_ld_wait();
+            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
+            softmax_chunk(rn, c + 1);
+          }
+        }
+        for (int c = n_live; c < n_chunks; ++c) {  // keys masked for the whole warp (causal): P = 0
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = 0u;
           tmem_st_32x32b_x16(taddr + c * 16, pk);
         }
         tmem_st_wait();
