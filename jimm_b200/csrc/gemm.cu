@@ -47,6 +47,12 @@ static constexpr int EPI_BUF_BYTES = 32 * 128;                     // one 32-row
 static constexpr int EPI_STAGE_BYTES = EPI_WARPS * EPI_BUF_BYTES;  // 32 KB (the generic path uses 4 x 4608 B of it)
 static constexpr int BIAS_BYTES = BN * 4;                          // per-tile bias copy
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BIAS_BYTES + 256 + 1024;
+// CTA-pair mode (cta_group::2): the pair computes a 256 x 256 tile; each CTA stages its own 128 A rows and HALF of the B
+// rows (128) per k-block -> 32 KB stages, 6 of them; the B operand traffic from L2 and the smem fill per SM drop by a third.
+static constexpr int P_STAGES = 6;
+static constexpr int P_B_STAGE_BYTES = (BN / 2) * 128;
+static constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;
+static_assert(P_STAGES * P_STAGE_BYTES == STAGES * STAGE_BYTES, "pair and single modes share the smem carve-up");
 static constexpr int NUM_THREADS = 384;
 static constexpr uint32_t TMEM_COLS = 512;
 static_assert(4 * 32 * EPI_PITCH * 4 <= EPI_STAGE_BYTES, "staging region too small");
@@ -273,32 +279,38 @@ __device__ __noinline__ void epilogue_generic(const EpiDev& epi, uint32_t taddr,
   }
 }
 
-template <typename T, int OUT, int ACT>
+template <typename T, int OUT, int ACT, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const EpiDev epi, int K) {
   constexpr int BK = 128 / sizeof(T);  // one 128-byte swizzle atom along K per stage
   constexpr int UK = 32 / sizeof(T);   // UMMA K (16 for 16-bit, 8 for tf32)
-  constexpr uint32_t IDESC = make_idesc(Traits<T>::FMT, BM, BN);
+  constexpr uint32_t IDESC = make_idesc(Traits<T>::FMT, PAIR ? 2 * BM : BM, BN);
+  constexpr int NSTAGE = PAIR ? P_STAGES : STAGES;
+  constexpr int B_BYTES = PAIR ? P_B_STAGE_BYTES : B_STAGE_BYTES;
+  constexpr int TILE_M = PAIR ? 2 * BM : BM;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* smem_b = smem + NSTAGE * A_STAGE_BYTES;
   uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
   float* sbias = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES + BIAS_BYTES);
-  uint64_t* full_bar = bars;                    // [STAGES]
-  uint64_t* empty_bar = bars + STAGES;          // [STAGES]
-  uint64_t* tmem_full_bar = bars + 2 * STAGES;  // [2]
+  uint64_t* full_bar = bars;                    // [NSTAGE]
+  uint64_t* empty_bar = bars + NSTAGE;          // [NSTAGE]
+  uint64_t* tmem_full_bar = bars + 2 * NSTAGE;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2; // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int M = epi.M, N = epi.N;
-  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
+  const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = (K + BK - 1) / BK;
   const bool dbg_no_epi = (epi.debug & 1) != 0, dbg_no_load = (epi.debug & 2) != 0;  // bring-up probes (JIMM_GEMM_DEBUG)
 
@@ -308,19 +320,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if constexpr (OUT != OUT_GENERIC) tma_prefetch_desc(&map_c);
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < NSTAGE; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], EPI_WARPS);
+      mbar_init(&tmem_empty_bar[a], PAIR ? 2 * EPI_WARPS : EPI_WARPS);  // pair: both CTAs' epilogues release the leader's MMA
     }
     fence_barrier_init();
   }
-  if (warp_idx == 2) tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  if (warp_idx == 2) {
+    if constexpr (PAIR) tmem_alloc_pair(tmem_ptr_smem, TMEM_COLS);
+    else tmem_alloc(tmem_ptr_smem, TMEM_COLS);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before any remote arrive / multicast commit
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -329,29 +345,40 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          if (dbg_no_load) {
+          if constexpr (PAIR) {
+            // both CTAs credit the LEADER's full barrier; only the leader arms it (with the bytes of both CTAs)
+            const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (cta_rank == 0) {
+              if (dbg_no_load) mbar_arrive(&full_bar[stage]);
+              else mbar_arrive_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+            }
+            if (!dbg_no_load) {
+              tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &map_a, full_leader, kb * BK, m_blk * TILE_M + static_cast<int>(cta_rank) * BM);
+              tma_load_2d_pair(smem_b + stage * B_BYTES, &map_b, full_leader, kb * BK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+            }
+          } else if (dbg_no_load) {
             mbar_arrive(&full_bar[stage]);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-            tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(smem_b + stage * B_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (pair mode: the leader CTA only) =====================
+    if (lane == 0 && cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -359,16 +386,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t adesc = make_umma_desc_sw128(a_addr + k * 32);
             const uint64_t bdesc = make_umma_desc_sw128(b_addr + k * 32);
-            umma_ss<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (PAIR) umma_ss_pair<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+            else umma_ss<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above retire
-          if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if constexpr (PAIR) {
+            tcgen05_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs once the MMAs above retire
+            if (kb == num_kb - 1) tcgen05_commit_pair(&tmem_full_bar[acc]);
+          } else {
+            tcgen05_commit(&empty_bar[stage]);
+            if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc]);
+          }
+          if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -379,9 +412,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int half = (warp_idx - 4) >> 2;  // column half of the 256-wide accumulator this warp drains
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
-      const int row_base = m_blk * BM + q * 32;
+      const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BM + q * 32;
       if constexpr (OUT != OUT_GENERIC) {
         // per-tile bias copy (one coalesced 128-bit load per lane of two warps), overlapped with the wait for the MMAs
         named_bar_sync(1, EPI_WARPS * 32);  // every epilogue warp is done with the previous tile's bias
@@ -406,7 +440,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
+        else mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if constexpr (OUT != OUT_GENERIC) {
@@ -415,9 +452,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair's MMAs / remote arrives are in flight
+  else __syncthreads();
   tcgen05_fence_after();
-  if (warp_idx == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp_idx == 2) {
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -532,6 +573,7 @@ int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void
   if (int rc = check_epi(epi, N)) return rc;
   if (int rc = make_map(&plan->map_a, dtype, A, M, K, lda, BM)) return rc;
   if (int rc = make_map(&plan->map_b, dtype, B, N, K, ldb, BN)) return rc;
+  if (int rc = make_map(&plan->map_b_pair, dtype, B, N, K, ldb, BN / 2)) return rc;
   plan->M = M; plan->N = N; plan->K = K; plan->dtype = dtype; plan->epi = epi;
   memset(&plan->map_c, 0, sizeof(plan->map_c));
   if (plan->epi.mode == 2) {
@@ -563,16 +605,46 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   return d;
 }
 
+static int pair_mode_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* env = getenv("JIMM_GEMM_PAIR"); v = env ? atoi(env) : 1; }
+  return v;
+}
+
 template <typename T, int OUT, int ACT>
 static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((p->N + BN - 1) / BN);
+  const int n_tiles = (p->N + BN - 1) / BN;
+  const EpiDev d = to_dev(p->epi, M, p->N);
+  if (OUT != OUT_GENERIC && pair_mode_enabled() && M >= 512) {
+    // CTA pairs: 256 x 256 tiles, cluster (2,1,1), one pair per two SMs
+    const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * n_tiles;
+    const int max_pairs = device_sm_count() / 2;
+    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    JIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, OUT, ACT, true>, p->map_a, p->map_b_pair, p->map_c, d, p->K));
+    note_launch();
+    return 0;
+  }
+  const int tiles = ((M + BM - 1) / BM) * n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_tcgen05_kernel<T, OUT, ACT><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, to_dev(p->epi, M, p->N), p->K);
+  gemm_tcgen05_kernel<T, OUT, ACT, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, d, p->K);
   JIMM_LAUNCH_CHECK();
   return 0;
 }

@@ -37,7 +37,7 @@ struct GemmEpilogue {
 };
 
 struct GemmPlan {
-  CUtensorMap map_a, map_b, map_c;  // map_c: output (mode 2 only)
+  CUtensorMap map_a, map_b, map_b_pair, map_c;  // map_b_pair: 128-row B box (CTA-pair mode); map_c: output (mode 2 only)
   int M = 0, N = 0, K = 0;
   int dtype = DT_F16;  // operand type: DT_F16 / DT_BF16 / DT_F32 (tf32 MMA)
   GemmEpilogue epi;

@@ -26,7 +26,7 @@ def run(M, N, K, dtype, mode):
     out = gemm(lib, A, B, mode=mode)
     torch.cuda.synchronize()
     e = rel_err(out, ref)
-    print(f"M={M} N={N} K={K} {dtype} mode={mode}: rel err {e:.3e}", flush=True)
+    print(f"M={M} N={N} K={K} {dtype} mode={mode}: rel err {e:.3e}" + (" BAD" if e > 1e-4 else ""), flush=True)
     if e > 1e-4:
         d = (out.double() - ref).abs()
         bm, bn = min(M, 32), min(N, 32)
@@ -46,7 +46,7 @@ def run(M, N, K, dtype, mode):
 worst = 0.0
 if not os.environ.get("PERF_ONLY"):
     for dtype in (torch.float16, torch.bfloat16, torch.float32):
-        for (M, N, K) in ((128, 256, 64), (128, 256, 256), (256, 512, 768), (1000, 1000, 512)):
+        for (M, N, K) in ((128, 256, 64), (128, 256, 256), (256, 512, 768), (1000, 1000, 512), (1024, 512, 256), (3000, 1000, 512)):
             for mode in (0, 1, 2):
                 worst = max(worst, run(M, N, K, dtype, mode))
     print("WORST", worst)

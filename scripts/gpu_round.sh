@@ -16,6 +16,9 @@ for s in $STAGES; do
     benchref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?" ;;
     probe)   for d in 0 1 2 3; do echo "== JIMM_GEMM_DEBUG=$d"; JIMM_GEMM_DEBUG=$d PERF_ONLY=1 MODES=2 timeout 120 python scripts/gpu_debug_gemm.py 2>&1 | grep perf; done > gpurun_out/probe.log 2>&1; echo "probe rc=$?" ;;
     ncu_src) timeout 600 ncu --set full --section SourceCounters --clock-control none --import-source on -k regex:gemm_tcgen05 -s 3 -c 2 -o gpurun_out/prof_gemm_src -f env PERF_ONLY=1 MODES=2 python scripts/gpu_debug_gemm.py > gpurun_out/ncu_src.log 2>&1; echo "ncu_src rc=$?" ;;
+    attnperf) timeout 200 python scripts/gpu_attn_perf.py > gpurun_out/attn_perf.log 2>&1; JIMM_ATTN_IMPL=flash timeout 200 python scripts/gpu_attn_perf.py >> gpurun_out/attn_perf.log 2>&1; echo "attnperf rc=$?"; cat gpurun_out/attn_perf.log ;;
+    ncu_attn) NCU=1 timeout 600 ncu --set full --section SourceCounters --clock-control none --import-source on -k regex:attention_tc -s 3 -c 1 -o gpurun_out/prof_attn -f python scripts/gpu_attn_perf.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu_attn rc=$?" ;;
+    pairprobe) for pm in 0 1; do echo "== JIMM_GEMM_PAIR=$pm"; JIMM_GEMM_PAIR=$pm MODES=2 timeout 200 python scripts/gpu_debug_gemm.py 2>&1 | grep -E "perf|WORST|BAD|best matches"; done > gpurun_out/pairprobe.log 2>&1; echo "pairprobe rc=$?"; cat gpurun_out/pairprobe.log ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/ncu_list.log 2>&1; echo "ncu_list rc=$?" ;;
     ncu_full) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 20 -c 4 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 1 --no-cpu > gpurun_out/ncu_full.log 2>&1; echo "ncu_full rc=$?" ;;
   esac
