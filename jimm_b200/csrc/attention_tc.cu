@@ -288,7 +288,9 @@ static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int
 
 // Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
 int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
-  if (S > 256 || S < 1) return 1;
+  // One query tile (S <= 128) leaves half of the softmax warps idle: the flash kernel is as fast or faster there (measured:
+  // S=50 39 us vs 25 us, S=77 causal 35 vs 37 us; S=197 128 vs 218 us, S=256 140 vs 215 us at B=256).
+  if (S > 256 || S <= 128) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
   if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, B, S, H, causal, stream);
   if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, B, S, H, causal, stream);

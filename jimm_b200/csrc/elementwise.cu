@@ -102,7 +102,7 @@ int layernorm_run(const float* x, int ldx, int group, int row_off, const int* ro
 // ------------------------------------------------------------------------------------------
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int H, int W, int C, int P, int gh, int gw, size_t total4) {
+patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int H, int W, int C, int P, int gh, int gw, size_t total4, int rps) {
   const size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i4 >= total4) return;
   const size_t e = i4 * 4;
@@ -123,7 +123,7 @@ patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int 
     const InT* h = reinterpret_cast<const InT*>(&t);
     for (int j = 0; j < 4; ++j) v[j] = to_float(h[j]);
   }
-  const size_t dst = (static_cast<size_t>(b) * gh * gw + static_cast<size_t>(gy) * gw + gx) * (static_cast<size_t>(P) * PC) +
+  const size_t dst = (static_cast<size_t>(b) * rps + static_cast<size_t>(gy) * gw + gx) * (static_cast<size_t>(P) * PC) +
                      static_cast<size_t>(ky) * PC + kc;
   if constexpr (std::is_same<OutT, tf32_t>::value) {
     *reinterpret_cast<float4*>(out + dst) = make_float4(round_tf32(v[0]), round_tf32(v[1]), round_tf32(v[2]), round_tf32(v[3]));
@@ -139,29 +139,53 @@ patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int 
 }
 
 template <typename InT>
-static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream) {
+static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rps) {
   const int gh = H / P, gw = W / P;
+  if (rps <= 0) rps = gh * gw;
   const size_t total4 = static_cast<size_t>(B) * H * W * C / 4;
   const int threads = 256;
   const unsigned grid = static_cast<unsigned>((total4 + threads - 1) / threads);
   const InT* in = static_cast<const InT*>(img);
-  if (out_type == DT_F32) patchify_kernel<InT, float><<<grid, threads, 0, stream>>>(in, static_cast<float*>(out), B, H, W, C, P, gh, gw, total4);
-  else if (out_type == DT_TF32) patchify_kernel<InT, tf32_t><<<grid, threads, 0, stream>>>(in, static_cast<tf32_t*>(out), B, H, W, C, P, gh, gw, total4);
-  else if (out_type == DT_F16) patchify_kernel<InT, __half><<<grid, threads, 0, stream>>>(in, static_cast<__half*>(out), B, H, W, C, P, gh, gw, total4);
-  else patchify_kernel<InT, __nv_bfloat16><<<grid, threads, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), B, H, W, C, P, gh, gw, total4);
+  if (out_type == DT_F32) patchify_kernel<InT, float><<<grid, threads, 0, stream>>>(in, static_cast<float*>(out), B, H, W, C, P, gh, gw, total4, rps);
+  else if (out_type == DT_TF32) patchify_kernel<InT, tf32_t><<<grid, threads, 0, stream>>>(in, static_cast<tf32_t*>(out), B, H, W, C, P, gh, gw, total4, rps);
+  else if (out_type == DT_F16) patchify_kernel<InT, __half><<<grid, threads, 0, stream>>>(in, static_cast<__half*>(out), B, H, W, C, P, gh, gw, total4, rps);
+  else patchify_kernel<InT, __nv_bfloat16><<<grid, threads, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), B, H, W, C, P, gh, gw, total4, rps);
   JIMM_LAUNCH_CHECK();
   return 0;
 }
 
-int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream) {
+int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rows_per_sample) {
   if ((P * C) % 4 != 0 || (W * C) % 4 != 0) {
     set_last_error("patchify: patch_size*channels (%d) and width*channels (%d) must be multiples of 4", P * C, W * C);
     return -1;
   }
   if (B <= 0) return 0;
-  if (in_type == DT_F32) return patchify_dispatch<float>(img, B, H, W, C, P, out, out_type, stream);
-  if (in_type == DT_F16) return patchify_dispatch<__half>(img, B, H, W, C, P, out, out_type, stream);
-  return patchify_dispatch<__nv_bfloat16>(img, B, H, W, C, P, out, out_type, stream);
+  if (in_type == DT_F32) return patchify_dispatch<float>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);
+  if (in_type == DT_F16) return patchify_dispatch<__half>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);
+  return patchify_dispatch<__nv_bfloat16>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+tokens_init_kernel(float4* __restrict__ x, const float4* __restrict__ cls, const float4* __restrict__ pos, size_t total4, int SD4, int D4) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int r = static_cast<int>(i % SD4);  // position inside the sample
+  float4 v = __ldg(pos + r);
+  if (cls != nullptr && r < D4) {
+    const float4 c = __ldg(cls + r);
+    v.x += c.x; v.y += c.y; v.z += c.z; v.w += c.w;
+  }
+  x[i] = v;
+}
+int tokens_init_run(float* x, const float* cls, const float* pos, int B, int S, int D, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  if (D % 4 != 0) { set_last_error("tokens_init: D must be a multiple of 4"); return -1; }
+  const size_t total4 = static_cast<size_t>(B) * S * D / 4;
+  tokens_init_kernel<<<static_cast<unsigned>((total4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(cls),
+                                                                                         reinterpret_cast<const float4*>(pos), total4, S * D / 4, D / 4);
+  JIMM_LAUNCH_CHECK();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

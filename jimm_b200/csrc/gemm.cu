@@ -68,6 +68,7 @@ struct EpiDev {
   int act, ldr, out_type, ldo, rows_in, rows_out, row_off, mode;
   int M, N;
   int debug;
+  int tok_pad, tok_off;  // > 0: 3-D token-scatter reduce-add (see GemmEpilogue)
   int vec;  // 1: N / ldo / ldr multiples of 4 and 16-byte aligned pointers -> vector accesses allowed (generic path)
 };
 
@@ -190,8 +191,16 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if constexpr (OUT == OUT_F32_ADD) tma_reduce_add_2d(map_c, tbuf_u32, n0, row_base);
-      else tma_store_2d(map_c, tbuf_u32, n0, row_base);
+      if constexpr (OUT == OUT_F32_ADD) {
+        if (epi.tok_pad > 0) {
+          const int b = row_base / epi.tok_pad;
+          tma_reduce_add_3d(map_c, tbuf_u32, n0, row_base - b * epi.tok_pad + epi.tok_off, b);
+        } else {
+          tma_reduce_add_2d(map_c, tbuf_u32, n0, row_base);
+        }
+      } else {
+        tma_store_2d(map_c, tbuf_u32, n0, row_base);
+      }
       tma_store_commit();
     }
   }
@@ -537,6 +546,20 @@ static int make_map(CUtensorMap* map, int dtype, const void* ptr, int rows, int 
   return 0;
 }
 
+// 3-D fp32 tensor map over out[B, S, N] (dims {N, S, B}), box {32 cols, 32 rows, 1}, SWIZZLE_128B
+static int make_map_3d_f32(CUtensorMap* map, const void* ptr, int B, int S, int N, int ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -3;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(S) * ld * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", static_cast<int>(r)); return -3; }
+  return 0;
+}
+
 int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows) {
   return make_map(map, dtype, ptr, rows, cols, ld, box_rows);
 }
@@ -583,7 +606,10 @@ int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void
                     (static_cast<size_t>(epi.ldo) * es) % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.out) & 15) == 0 &&
                     (epi.bias == nullptr || ((reinterpret_cast<uintptr_t>(epi.bias) & 15) == 0 && N % 4 == 0)) &&
                     !(epi.residual && epi.act != ACT_NONE);
-    if (ok) {
+    if (ok && epi.tok_pad > 0) {
+      if (epi.tok_pad % 32 != 0 || M % epi.tok_pad != 0 || !epi.residual) { set_last_error("gemm: bad token-scatter epilogue"); return -1; }
+      if (int rc = make_map_3d_f32(&plan->map_c, epi.out, M / epi.tok_pad, epi.tok_S, N, epi.ldo)) return rc;
+    } else if (ok) {
       if (int rc = make_map(&plan->map_c, epi.out_type, epi.out, M, N, epi.ldo, 32)) return rc;
     } else {
       plan->epi.mode = 0;
@@ -598,6 +624,7 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.act = e.act; d.ldr = e.ldr; d.out_type = e.out_type; d.ldo = e.ldo;
   d.rows_in = e.rows_in; d.rows_out = e.rows_out; d.row_off = e.row_off; d.mode = e.mode;
   d.M = M; d.N = N;
+  d.tok_pad = e.tok_pad; d.tok_off = e.tok_off;
   d.vec = epi_vec_ok(e, N);
   static int dbg = -1;
   if (dbg < 0) { const char* env = getenv("JIMM_GEMM_DEBUG"); dbg = env ? atoi(env) : 0; }

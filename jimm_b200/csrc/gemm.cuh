@@ -29,6 +29,10 @@ struct GemmEpilogue {
   void* out = nullptr;
   int out_type = DT_F32;
   int ldo = 0;                                   // output row stride (elements)
+  // Token-scatter form of the fp32 reduce-add epilogue (patch embedding): A rows are (sample, padded patch index) with
+  // tok_pad rows per sample (multiple of 32); row (b, p) is ADDED to out[b, p + tok_off, :] of a [B, tok_S, N] tensor through a
+  // 3-D tensor map (rows p + tok_off >= tok_S are clipped by TMA).  Requires residual == out (pre-initialised with pos-emb).
+  int tok_pad = 0, tok_off = 0, tok_S = 0;
   int rows_in = 0, rows_out = 0, row_off = 0;    // out_row = (r / rows_in) * rows_out + r % rows_in + row_off (rows_in == 0: identity)
   // 2: TMA epilogue (swizzled smem box -> cp.async.bulk.tensor store, cp.reduce .add for the fp32 residual stream; needs
   //    no rowadd / row remap and residual == out) -- falls back to 0 when not applicable;

@@ -16,7 +16,12 @@ int layernorm_run(const float* x, int ldx, int group, int row_off, const int* ro
 
 // Patchify: NHWC image (in_type fp32/fp16/bf16) -> A matrix [B*gh*gw, P*P*C] of out_type, row order (b,gy,gx), column
 // order (ky,kx,c) == the HWIO kernel reshape (common/vit.py:153-165,228-230).  128-bit loads.
-int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream);
+int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream,
+                 int rows_per_sample = 0 /* 0 = gh*gw; larger = padded row count per sample (pad rows untouched) */);
+
+// x[b, s, :] = pos[s, :] (+ cls for s == 0)   -- initial value of the residual stream; the patch GEMM then reduce-adds the
+// patch embeddings into rows tok_off.. (common/vit.py:231-236)
+int tokens_init_run(float* x, const float* cls, const float* pos, int B, int S, int D, cudaStream_t stream);
 
 // x[b, 0, :] = cls + pos[0]   (common/vit.py:231-236), fp32 residual stream [B, S, D]
 int cls_row_run(float* x, const float* cls, const float* pos, int B, int S, int D, cudaStream_t stream);

@@ -105,7 +105,8 @@ struct Encoder {
 
 struct VisionTower {
   bool present = false;
-  int img = 0, P = 0, C = 0, D = 0, n = 0, S = 0, pooling = 0, pre_norm = 0, patch_bias = 0;
+  int img = 0, P = 0, C = 0, D = 0, n = 0, n_pad = 0, S = 0, pooling = 0, pre_norm = 0, patch_bias = 0;
+  bool patch_scatter = false;  // patch GEMM reduce-adds into the pos-initialised residual stream through a 3-D TMA map
   float eps_outer = 1e-5f;
   Encoder enc;
   LinearW patch;
@@ -392,9 +393,15 @@ static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float
   Workspace& ws = m->ws;
   const int D = v.D, S = v.S, n = v.n;
   // patch embed + pos (+cls)
-  JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s));
-  JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * n, s));
-  if (v.pooling == JIMM_POOL_CLS) JIMM_TRY(cls_row_run(ws.x, v.cls, v.pos, B, S, D, s));
+  if (v.patch_scatter) {
+    JIMM_TRY(tokens_init_run(ws.x, v.pooling == JIMM_POOL_CLS ? v.cls : nullptr, v.pos, B, S, D, s));
+    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s, v.n_pad));
+    JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * v.n_pad, s));
+  } else {
+    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s));
+    JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * n, s));
+    if (v.pooling == JIMM_POOL_CLS) JIMM_TRY(cls_row_run(ws.x, v.cls, v.pos, B, S, D, s));
+  }
   if (v.pre_norm) JIMM_TRY(layernorm_run(ws.x, D, 1, 0, nullptr, v.ln_pre.scale, v.ln_pre.bias, v.eps_outer, ws.x, DT_F32, D, B * S, D, s));
   JIMM_TRY(run_encoder(m, &v.enc, B, S, s));
   if (v.pooling == JIMM_POOL_CLS) {
@@ -563,6 +570,8 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   v.n = (c.img_size / c.patch) * (c.img_size / c.patch);
   v.pooling = c.pooling; v.pre_norm = c.pre_norm; v.patch_bias = c.patch_bias; v.eps_outer = c.v_eps_outer;
   v.S = v.n + (v.pooling == JIMM_POOL_CLS ? 1 : 0);
+  v.n_pad = ((v.n + 31) / 32) * 32;
+  v.patch_scatter = !m->simt && m->epi_mode_res == 2;
   v.enc.c.D = c.v_width; v.enc.c.H = c.v_heads; v.enc.c.M = c.v_mlp; v.enc.c.L = c.v_layers;
   v.enc.c.act = c.v_act; v.enc.c.causal = 0; v.enc.c.eps = c.v_eps_block;
   const int D = v.D, PPC = c.patch * c.patch * c.in_ch;
@@ -636,7 +645,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   const size_t Bm = max_batch;
   size_t Tv = Bm * v.S, Dmax = D, x_elems = Tv * D, big_bytes = 0;
   auto upd = [&](size_t b) { if (b > big_bytes) big_bytes = b; };
-  upd(Bm * v.n * PPC * cs);              // patches
+  upd(Bm * v.n_pad * PPC * cs);          // patches (rows per sample padded to a multiple of 32)
   upd(Tv * 3 * D * 2);                   // qkv (16-bit)
   upd(Tv * static_cast<size_t>(c.v_mlp) * cs);  // MLP hidden
   if (v.pooling == JIMM_POOL_MAP) upd(Tv * 2 * D * 2);
@@ -667,7 +676,13 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   if ((rc = m->pool.alloc(&p, ws.out_dev_elems * sizeof(float)))) return rc; ws.out_dev = static_cast<float*>(p);
 
   // ---- GEMM plans (TMA descriptors bound to the fixed workspace / weight buffers) ----
-  {
+  if (v.patch_scatter) {
+    GemmEpilogue e;
+    e.bias = v.patch.b; e.residual = ws.x; e.ldr = D; e.out = ws.x; e.out_type = DT_F32; e.ldo = D; e.mode = 2;
+    e.tok_pad = v.n_pad; e.tok_off = v.pooling == JIMM_POOL_CLS ? 1 : 0; e.tok_S = v.S;
+    JIMM_TRY(gemm_plan_init(&v.p_patch, m->cdt, ws.big, PPC, v.patch.w, PPC, static_cast<int>(Bm) * v.n_pad, D, PPC, e));
+    if (v.p_patch.epi.mode != 2) { set_last_error("patch GEMM: token-scatter epilogue unavailable"); return JIMM_EINVAL; }
+  } else {
     GemmEpilogue e;
     e.bias = v.patch.b; e.rowadd = v.pos; e.out = ws.x; e.out_type = DT_F32; e.ldo = D;
     e.rows_in = v.n; e.rows_out = v.S; e.row_off = v.pooling == JIMM_POOL_CLS ? 1 : 0; e.mode = 0;

@@ -155,7 +155,7 @@ def _attn_ref(qkv, B, S, H, causal):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("S", [1, 16, 50, 64, 77, 197, 256, 577])
+@pytest.mark.parametrize("S", [1, 16, 50, 64, 77, 128, 129, 144, 197, 200, 256, 257, 577])
 @pytest.mark.parametrize("causal", [0, 1])
 def test_attention(lib, dtype, S, causal):
     B, H = 3, 2
@@ -169,7 +169,7 @@ def test_attention(lib, dtype, S, causal):
         assert rel_err(out, ref) < tol, (S, causal, out_dtype, rel_err(out, ref))
 
 
-@pytest.mark.parametrize("S,causal", [(50, 0), (77, 1), (197, 0), (256, 1)])
+@pytest.mark.parametrize("S,causal", [(130, 1), (197, 0), (256, 1)])
 def test_attention_flash_kernel_forced(lib, monkeypatch, S, causal):
     """S <= 256 normally takes the tcgen05 kernel; JIMM_ATTN_IMPL=flash keeps the mma.sync kernel covered there too."""
     monkeypatch.setenv("JIMM_ATTN_IMPL", "flash")

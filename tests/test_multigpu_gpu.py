@@ -1,0 +1,78 @@
+"""GPU (needs >= 2 B200s; skipped otherwise): the sharded contrastive head -- one process per GPU, embeddings exchanged by
+the fused normalise + NVLink peer-store + logits kernel (csrc/comm.cu) -- against the oracle's full logits, plus the
+torch.distributed all_gather baseline and repeated calls (epoch parity buffers)."""
+
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, kind, q):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    import jimm_oracle as O
+    from jimm_b200 import dist as jd
+    from jimm_b200.models import CLIP, SigLIP
+
+    jd.init_from_env("nccl")
+    tw = 128 if kind == "clip" else 256
+    cfg = O.DualCfg(64, 2, 256, 16, 20, 300, tw, tw // 64, 2)
+    p = O.random_dual_params(cfg, kind, seed=11)
+    Bg = 8 * world
+    img, txt = O.synthetic_images(Bg, 64), O.synthetic_tokens(Bg, 20, 300, kind)
+    with torch.no_grad():
+        ref = (O.clip_forward if kind == "clip" else O.siglip_forward)(p, cfg, img, txt)
+    cls = CLIP if kind == "clip" else SigLIP
+    m = cls(64, 2, 256, 16, 20, 300, tw, tw // 64, 2, dtype=torch.float16)
+    for k, v in p.items():
+        m.set_flat_param(k, v)
+    lo, hi = jd.shard_range(Bg, rank, world)
+    errs = []
+    for mode in ("peer", "peer", "peer", "nccl"):  # repeated peer calls exercise both parity buffers
+        m.set_comm(mode)
+        out = m(img[lo:hi].cuda(), txt[lo:hi].cuda())
+        assert out.shape == (hi - lo, Bg)
+        errs.append(float((out.cpu().double() - ref[lo:hi].double()).abs().max() / ref.abs().max()))
+    torch.cuda.synchronize()
+    dist.barrier()
+    q.put((rank, errs))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind", ["clip", "siglip"])
+@pytest.mark.timeout(600)
+def test_sharded_contrastive_head(kind):
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=500) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, errs in res:
+        assert all(e < 1e-3 for e in errs), (rank, errs)
