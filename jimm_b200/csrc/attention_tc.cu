@@ -132,7 +132,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
       if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
       // warp-uniform upper bound of keys any row of this warp needs (rows >= S are clamped: finite garbage, never stored)
       const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
-      const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32;
+      const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
+      const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
@@ -140,25 +141,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         mbar_wait(&s_full[t], sp);
         tcgen05_fence_after();
         // ---- pass 1: row max (next chunk's TMEM load in flight while this one is reduced) ----
+        // Chunks below n_full hold only valid keys for every lane of the warp: no per-element masking there.
         float m = -INFINITY;
         uint32_t r[32], rn[32];
+        auto max_chunk = [&](const uint32_t (&sv)[32], int c) {
+          if (c < n_full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float v = __uint_as_float(sv[j]);
+              m = (c * 32 + j < kmax) ? fmaxf(m, v) : m;
+            }
+          }
+        };
         tmem_ld_32x32b_x32(taddr, r);
         for (int c = 0; c < n_live; c += 2) {
           tmem_ld_wait();
           if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float v = __uint_as_float(r[j]);
-            m = (c * 32 + j < kmax) ? fmaxf(m, v) : m;
-          }
+          max_chunk(r, c);
           if (c + 1 < n_live) {
             tmem_ld_wait();
             if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(rn[j]);
-              m = ((c + 1) * 32 + j < kmax) ? fmaxf(m, v) : m;
-            }
+            max_chunk(rn, c + 1);
           }
         }
         const float moff = m * p.scale_log2;
@@ -166,17 +172,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         // P chunk c (16 columns) lands on S columns [16c, 16c+16) which belong to S chunk c/2 <= c: already in registers.
         // With the one-chunk-ahead prefetch S chunk c+1 is read BEFORE P chunk c is stored, and 16(c)+16 <= 32(c+1), so the
         // store never clobbers a chunk that has not been loaded yet.
-        float l = 0.f;
+        float2 l2 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), mo2 = make_float2(-moff, -moff);
         auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
           uint32_t pk[16];
+          if (c < n_full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), p.scale_log2, -moff));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), p.scale_log2, -moff));
-            p0 = (c * 32 + j < kmax) ? p0 : 0.f;
-            p1 = (c * 32 + j + 1 < kmax) ? p1 : 0.f;
-            l += p0 + p1;
-            pk[j >> 1] = pack2(p0, p1, FMT == 0 ? 1 : 2);
+            for (int j = 0; j < 32; j += 2) {
+              const float2 a = ffma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, mo2);
+              const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+              l2 = fadd2(l2, e);
+              pk[j >> 1] = pack2(e.x, e.y, FMT == 0 ? 1 : 2);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float2 a = ffma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, mo2);
+              float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+              e.x = (c * 32 + j < kmax) ? e.x : 0.f;
+              e.y = (c * 32 + j + 1 < kmax) ? e.y : 0.f;
+              l2 = fadd2(l2, e);
+              pk[j >> 1] = pack2(e.x, e.y, FMT == 0 ? 1 : 2);
+            }
           }
           tmem_st_32x32b_x16(taddr + c * 16, pk);
         };
@@ -191,6 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
             softmax_chunk(rn, c + 1);
           }
         }
+        const float l = l2.x + l2.y;
         for (int c = n_live; c < n_chunks; ++c) {  // keys masked for the whole warp (causal): P = 0
           uint32_t pk[16];
 #pragma unroll

@@ -46,11 +46,18 @@ def _worker(rank, world, port, kind, q):
     for k, v in p.items():
         m.set_flat_param(k, v)
     lo, hi = jd.shard_range(Bg, rank, world)
+    # single-GPU result of the whole batch on this rank: the sharded path must reproduce its row block bit for bit
+    m.set_comm("off")
+    full = m(img.cuda(), txt.cuda()).cpu()
     errs = []
     for mode in ("peer", "peer", "peer", "nccl"):  # repeated peer calls exercise both parity buffers
         m.set_comm(mode)
         out = m(img[lo:hi].cuda(), txt[lo:hi].cuda())
         assert out.shape == (hi - lo, Bg)
+        if mode == "peer":
+            assert torch.equal(out.cpu(), full[lo:hi]), "fused peer-memory head differs from the single-GPU head"
+        else:
+            assert float((out.cpu() - full[lo:hi]).abs().max()) < 1e-4
         errs.append(float((out.cpu().double() - ref[lo:hi].double()).abs().max() / ref.abs().max()))
     torch.cuda.synchronize()
     dist.barrier()
@@ -75,4 +82,4 @@ def test_sharded_contrastive_head(kind):
         p.join(120)
         assert p.exitcode == 0
     for rank, errs in res:
-        assert all(e < 1e-3 for e in errs), (rank, errs)
+        assert all(e < 2e-3 for e in errs), (rank, errs)  # fp16 towers x exp(logit_scale); the exact check is vs the single-GPU head
