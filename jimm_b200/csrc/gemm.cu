@@ -49,10 +49,13 @@ static constexpr int BIAS_BYTES = BN * 4;                          // per-tile b
 static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BIAS_BYTES + 256 + 1024;
 // CTA-pair mode (cta_group::2): the pair computes a 256 x 256 tile; each CTA stages its own 128 A rows and HALF of the B
 // rows (128) per k-block -> 32 KB stages, 6 of them; the B operand traffic from L2 and the smem fill per SM drop by a third.
-static constexpr int P_STAGES = 6;
+// Five of them, which frees 32 KB to double-buffer the epilogue's TMA-store boxes (wait_group.read 1 instead of 0).
+static constexpr int P_STAGES = 5;
 static constexpr int P_B_STAGE_BYTES = (BN / 2) * 128;
 static constexpr int P_STAGE_BYTES = A_STAGE_BYTES + P_B_STAGE_BYTES;
-static_assert(P_STAGES * P_STAGE_BYTES == STAGES * STAGE_BYTES, "pair and single modes share the smem carve-up");
+static constexpr int P_EPI_BUFS = 2;
+static_assert(P_STAGES * P_STAGE_BYTES + P_EPI_BUFS * EPI_WARPS * EPI_BUF_BYTES == STAGES * STAGE_BYTES + EPI_STAGE_BYTES,
+              "pair and single modes share the smem carve-up");
 static constexpr int NUM_THREADS = 384;
 static constexpr uint32_t TMEM_COLS = 512;
 static_assert(4 * 32 * EPI_PITCH * 4 <= EPI_STAGE_BYTES, "staging region too small");
@@ -136,13 +139,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // ---- TMA epilogue for one 128 x 128 half-tile owned by one epilogue warp's lane quarter (thread = row) ------------
 // 16-bit outputs: 64 columns per 32 x 128 B box (two x32 TMEM loads); 32-bit outputs: 32 columns per box.
-template <int OUT, int ACT>
-__device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const EpiDev& epi, uint32_t taddr, const float* sbias, uint8_t* tbuf,
-                                             int lane, int row_base, int n_tile0, int c_begin) {
+template <int OUT, int ACT, int NBUF>
+__device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const EpiDev& epi, uint32_t taddr, const float* sbias, uint8_t* tbuf0,
+                                             int lane, int row_base, int n_tile0, int c_begin, uint32_t& box_count) {
   constexpr bool OUT16 = (OUT == OUT_H16 || OUT == OUT_BF16);
   constexpr int COLS_PER_BOX = OUT16 ? 64 : 32;
   const int N = epi.N;
-  const uint32_t tbuf_u32 = smem_u32(tbuf);
   uint32_t r[32], r2[32], pk[32];
   if (n_tile0 + c_begin < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
 #pragma unroll 1
@@ -183,7 +185,13 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
       if (more) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch the next box
     }
     // ---- stage + TMA store ----
-    if (lane == 0) tma_store_wait_read();  // the previous box of this warp has been read out of smem
+    uint8_t* tbuf = tbuf0 + (NBUF > 1 ? (box_count & (NBUF - 1)) * EPI_BUF_BYTES : 0);
+    const uint32_t tbuf_u32 = smem_u32(tbuf);
+    ++box_count;
+    if (lane == 0) {  // the box that last used this buffer has been read out of smem
+      if constexpr (NBUF > 1) tma_store_wait_read1();
+      else tma_store_wait_read();
+    }
     __syncwarp();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -303,9 +311,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + NSTAGE * A_STAGE_BYTES;
-  uint8_t* epi_stage = smem + STAGES * STAGE_BYTES;
-  float* sbias = reinterpret_cast<float*>(epi_stage + EPI_STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_STAGE_BYTES + BIAS_BYTES);
+  uint8_t* epi_stage = smem + (PAIR ? P_STAGES * P_STAGE_BYTES : STAGES * STAGE_BYTES);
+  constexpr int EPI_BUFS = PAIR ? P_EPI_BUFS : 1;
+  constexpr int EPI_REGION = EPI_BUFS * EPI_STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(epi_stage + EPI_REGION);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + EPI_REGION + BIAS_BYTES);
   uint64_t* full_bar = bars;                    // [NSTAGE]
   uint64_t* empty_bar = bars + NSTAGE;          // [NSTAGE]
   uint64_t* tmem_full_bar = bars + 2 * NSTAGE;  // [2]
@@ -420,7 +430,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int q = warp_idx & 3;            // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
     const int half = (warp_idx - 4) >> 2;  // column half of the 256-wide accumulator this warp drains
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, box_count = 0;
     const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
@@ -442,7 +452,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (dbg_no_epi) {
       } else if constexpr (OUT != OUT_GENERIC) {
         if (row_base < M)
-          epilogue_tma<OUT, ACT>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUF_BYTES, lane, row_base, n_blk * BN, half * (BN / 2));
+          epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES, lane, row_base, n_blk * BN,
+                                           half * (BN / 2), box_count);
       } else {
         if (half == 0 && row_base < M)
           epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_blk * BN);
