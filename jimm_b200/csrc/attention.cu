@@ -89,6 +89,8 @@ attention_kernel(const T* __restrict__ qkv, OutT* __restrict__ out, int S, int H
   const uint32_t sK0 = sQ + QT * 128;
   const uint32_t sV0 = sK0 + 2 * KT * 128;
   const int q0 = qt * QT;
+  pdl_launch_dependents();
+  pdl_wait();
   int n_kv = (S + KT - 1) / KT;
   if (CAUSAL) n_kv = min(n_kv, qt + 1);
 
@@ -266,9 +268,9 @@ template <typename T, typename OutT>
 static int attn_launch(const void* qkv, void* out, int B, int S, int H, int causal, cudaStream_t stream) {
   dim3 grid((S + QT - 1) / QT, H, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  if (causal) attention_kernel<T, OutT, true><<<grid, 128, 0, stream>>>(static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2);
-  else attention_kernel<T, OutT, false><<<grid, 128, 0, stream>>>(static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2);
-  JIMM_LAUNCH_CHECK();
+  if (causal) JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, true>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2));
+  else JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, false>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2));
+  note_launch();
   return 0;
 }
 

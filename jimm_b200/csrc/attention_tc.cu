@@ -52,6 +52,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.B * p.H;
 
+  pdl_launch_dependents();
   if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -69,6 +70,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -298,9 +300,9 @@ static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     attr_set = true;
   }
-  if (causal) attention_tc_kernel<T, OutT, true><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(map, p);
-  else attention_tc_kernel<T, OutT, false><<<grid, ATC_THREADS, ATC_SMEM, stream>>>(map, p);
-  JIMM_LAUNCH_CHECK();
+  if (causal) JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, p));
+  else JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, p));
+  note_launch();
   return 0;
 }
 

@@ -21,6 +21,8 @@ layernorm_kernel(const float* __restrict__ x, size_t ldx, int group, int row_off
                  int rows, int D) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  pdl_wait();
   if (warp >= rows) return;
   const size_t src_row = static_cast<size_t>(warp) * group + (row_index ? row_index[warp] : row_off);
   const float4* xr = reinterpret_cast<const float4*>(x + src_row * ldx);
@@ -77,10 +79,12 @@ static int ln_launch(const float* x, int ldx, int group, int row_off, const int*
   const int grid = (rows + wpb - 1) / wpb;
   const int nv = D / 4;
   if (nv <= 32 * 8)
-    layernorm_kernel<OutT, 8><<<grid, threads, 0, stream>>>(x, ldx, group, row_off, row_index, scale, bias, eps, static_cast<OutT*>(out), ldy, rows, D);
+    JIMM_CUDA_CHECK(launch_k(layernorm_kernel<OutT, 8>, dim3(grid), dim3(threads), 0, stream, 1, true, x, ldx, group, row_off, row_index, scale, bias, eps,
+                             static_cast<OutT*>(out), ldy, rows, D));
   else
-    layernorm_kernel<OutT, 16><<<grid, threads, 0, stream>>>(x, ldx, group, row_off, row_index, scale, bias, eps, static_cast<OutT*>(out), ldy, rows, D);
-  JIMM_LAUNCH_CHECK();
+    JIMM_CUDA_CHECK(launch_k(layernorm_kernel<OutT, 16>, dim3(grid), dim3(threads), 0, stream, 1, true, x, ldx, group, row_off, row_index, scale, bias, eps,
+                             static_cast<OutT*>(out), ldy, rows, D));
+  note_launch();
   return 0;
 }
 

@@ -333,6 +333,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int num_kb = (K + BK - 1) / BK;
   const bool dbg_no_epi = (epi.debug & 1) != 0, dbg_no_load = (epi.debug & 2) != 0;  // bring-up probes (JIMM_GEMM_DEBUG)
 
+  pdl_launch_dependents();
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
@@ -358,6 +359,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -664,26 +666,16 @@ static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * n_tiles;
     const int max_pairs = device_sm_count() / 2;
     const int pairs = tiles < max_pairs ? tiles : max_pairs;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    JIMM_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<T, OUT, ACT, true>, p->map_a, p->map_b_pair, p->map_c, d, p->K));
+    JIMM_CUDA_CHECK(launch_k(gemm_tcgen05_kernel<T, OUT, ACT, true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, 2, true,
+                             p->map_a, p->map_b_pair, p->map_c, d, p->K));
     note_launch();
     return 0;
   }
   const int tiles = ((M + BM - 1) / BM) * n_tiles;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  gemm_tcgen05_kernel<T, OUT, ACT, false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(p->map_a, p->map_b, p->map_c, d, p->K);
-  JIMM_LAUNCH_CHECK();
+  JIMM_CUDA_CHECK(launch_k(gemm_tcgen05_kernel<T, OUT, ACT, false>, dim3(grid), dim3(NUM_THREADS), SMEM_BYTES, stream, 1, true, p->map_a,
+                           p->map_b, p->map_c, d, p->K));
+  note_launch();
   return 0;
 }
 

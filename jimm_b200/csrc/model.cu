@@ -38,6 +38,11 @@ void set_last_error(const char* fmt, ...) {
 }
 static std::atomic<long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* env = getenv("JIMM_PDL"); v = env ? atoi(env) : 1; }
+  return v;
+}
 
 #define JIMM_TRY(expr)          \
   do {                          \
@@ -819,30 +824,38 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   }
   const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
   const int od = vision_out_dim(m);
-  // Chunked double-buffered pipeline: the staging buffer (max_batch fp32 images) is split into two slots of `chunk` images;
-  // the H2D copy of chunk i+1 runs on the side stream while chunk i is in the tower.
-  int chunk = m->max_batch / 2;
-  static int chunk_cap = -1;
-  if (chunk_cap < 0) { const char* env = getenv("JIMM_HOST_CHUNK"); chunk_cap = (env && atoi(env) > 0) ? atoi(env) : 128; }
-  if (chunk > chunk_cap) chunk = chunk_cap;
-  const bool pipelined = chunk >= 16 && B > chunk;
-  if (!pipelined) chunk = m->max_batch;
-  const size_t slot_bytes = static_cast<size_t>(chunk) * m->vis.img * m->vis.img * m->vis.C * sizeof(float);
+  // Two-slot pipeline per super-chunk of <= max_batch images: a small first slice (1/4, so little copy time is exposed) and the
+  // rest; the H2D copy of the second slice runs on the side stream while the first slice is in the tower, and the next
+  // super-chunk's first copy overlaps this one's second forward.  The slots partition the staging buffer (max_batch fp32 images).
+  static int head_div = -1;
+  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
+  const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-  int ci = 0;
-  for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
-    const int nb = B - b0 < chunk ? B - b0 : chunk;
-    const int slot = pipelined ? (ci & 1) : 0;
-    uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + slot * slot_bytes;
-    float* out_d = m->ws.out_dev + static_cast<size_t>(slot) * chunk * od;
-    if (ci >= (pipelined ? 2 : 1)) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + b0 * img_bytes, nb * img_bytes, cudaMemcpyHostToDevice, m->copy_stream));
-    JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
-    JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
-    JIMM_TRY(run_vision(m, dst, in_dtype, nb, out_d, s));
-    JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, out_d, static_cast<size_t>(nb) * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  int uses[2] = {0, 0};
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    int c0 = nb;
+    if (nb >= 128) c0 = ((nb / head_div + 31) / 32) * 32;
+    const int sizes[2] = {c0, nb - c0};
+    int off = 0;
+    for (int slot = 0; slot < 2; ++slot) {
+      const int n = sizes[slot];
+      if (n <= 0) continue;
+      uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
+      float* out_d = m->ws.out_dev + static_cast<size_t>(off) * od;
+      if (uses[slot] > 0) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
+      JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + static_cast<size_t>(b0 + off) * img_bytes, n * img_bytes,
+                                      cudaMemcpyHostToDevice, m->copy_stream));
+      JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
+      JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
+      JIMM_TRY(run_vision(m, dst, in_dtype, n, out_d, s));
+      JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
+      ++uses[slot];
+      JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0 + off) * od, out_d, static_cast<size_t>(n) * od * sizeof(float),
+                                      cudaMemcpyDeviceToHost, s));
+      off += n;
+    }
   }
   return 0;
 }
