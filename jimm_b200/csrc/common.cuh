@@ -336,17 +336,28 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// jax.nn.gelu(approximate=True): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
-__device__ __forceinline__ float gelu_tanh(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * x * (1.0f + k1 * x * x);
-  // exact-ish tanh via exp: tanh(u) = 1 - 2/(exp(2u)+1); keeps ~1e-7 rel error (tanh.approx is ~5e-4)
-  float e = __expf(2.0f * u);
-  float t = 1.0f - __fdividef(2.0f, e + 1.0f);
-  return 0.5f * x * (1.0f + t);
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-// quickgelu: x * sigmoid(1.702 x)
-__device__ __forceinline__ float quick_gelu(float x) { return __fdividef(x, 1.0f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// jax.nn.gelu(approximate=True): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3).
+// Since 0.5 (1 + tanh(u)) == sigmoid(2u), gelu(x) = x / (1 + 2^(x * (c0 + c1 x^2))) with c0 = -2 sqrt(2/pi) log2(e),
+// c1 = c0 * 0.044715: 5 FP32 ops + MUFU.EX2 + MUFU.RCP per element (the first version spent ~12 ops; the FC1 epilogue was
+// ALU/MUFU-bound, profiles/r1_c).  ex2.approx / rcp.approx are accurate to ~2 ulp; x -> -inf gives -0, x -> +inf gives x.
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float c0 = -2.0f * 0.7978845608028654f * 1.4426950408889634f;
+  const float c1 = c0 * 0.044715f;
+  const float z = x * fmaf(x * x, c1, c0);
+  return x * rcp_fast(1.0f + ex2_fast(z));
+}
+// quickgelu: x * sigmoid(1.702 x)   (common/transformer.py:12-19)
+__device__ __forceinline__ float quick_gelu(float x) { return x * rcp_fast(1.0f + ex2_fast(x * (-1.702f * 1.4426950408889634f))); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
