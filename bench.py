@@ -122,6 +122,15 @@ def build_model(workload: str, dtype_name: str):
     raise SystemExit(f"unknown workload {workload}")
 
 
+def cpu_threads() -> int:
+    """Threads for the CPU arm: every host core up to 32 (torch's intra-op pool stops scaling -- and then regresses -- beyond
+    that on the 128-core GPU-box hosts for this model size; JIMM_CPU_THREADS overrides)."""
+    env = os.environ.get("JIMM_CPU_THREADS")
+    if env:
+        return max(1, int(env))
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def oracle_step_fn(workload: str, B: int):
     """The CPU arm: oracle restatement in torch fp32 with jimm semantics, same architecture / synthetic inputs."""
     import torch
@@ -129,7 +138,7 @@ def oracle_step_fn(workload: str, B: int):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import jimm_oracle as O
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     if workload == "vit_b16":
         cfg = O.ViTCfg()
         p = O.random_vit_params(cfg, seed=0)
@@ -172,7 +181,7 @@ def run_reference(args):
         return 0
     B = args.cpu_batch
     ips, ms = time_cpu(args.workload, B, args.steps, args.warmup)
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     sample = f"{B} images/step x {args.steps} steps of {WORKLOADS[args.workload][0]}"
     line = {
         "impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
@@ -283,7 +292,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cb = args.cpu_batch
         ips, _ = time_cpu(args.workload, cb, args.cpu_steps, 1)
-        cpu = {"value": ips, "unit": "images/sec", "cores": os.cpu_count() or 1, "kind": "port",
+        cpu = {"value": ips, "unit": "images/sec", "cores": cpu_threads(), "host_cores": os.cpu_count() or 1, "kind": "port",
                "sample": f"{cb} images/step x {args.cpu_steps} steps, oracle/jimm_oracle.py torch-CPU fp32 (jimm semantics)"}
 
     if rank == 0:
@@ -314,8 +323,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="vit_b16", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
-    ap.add_argument("--cpu-batch", type=int, default=8)
-    ap.add_argument("--cpu-steps", type=int, default=6)
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -278,7 +278,9 @@ int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, 
   if (B <= 0 || S <= 0) return 0;
   const char* env = getenv("JIMM_ATTN_IMPL");  // "flash" forces the mma.sync flash kernel (A/B comparison, bisection)
   if (!(env && strcmp(env, "flash") == 0)) {
-    const int rc = attention_tc_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
+    int rc = attention_tc_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
+    if (rc <= 0) return rc;
+    rc = attention_tc_long_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
     if (rc <= 0) return rc;
   }
   if (B > 65535 || H > 65535) { set_last_error("attention: grid too large (B=%d H=%d)", B, H); return -1; }

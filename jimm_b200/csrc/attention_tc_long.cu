@@ -1,0 +1,370 @@
+// tcgen05 softmax attention for sequences longer than 256 tokens (non-causal), head_dim 64:
+// ViT-L/16@384 (S = 576) and SigLIP2-L/16@512 (S = 1024) -- BASELINE configs 3 and 5.
+//
+// Two passes over the keys instead of online-softmax rescaling (the O accumulator lives in TMEM; rescaling it would cost a
+// TMEM round trip per key block): pass A recomputes S = Q K^T block by block only to find each row's maximum, pass B
+// recomputes S, writes P = exp2((S - max) * scale) over it in place (16-bit, tensor memory) and accumulates O += P V with
+// the tensor core's own accumulate flag.  The extra Q K^T costs 0.5x tensor work; the kernel is MUFU(exp2)-bound anyway.
+//
+// One persistent CTA per SM; work unit = (sample, head, pair of 128-row query tiles); keys in blocks of 192:
+//   warp 0   TMA: Q pair (256 x 128 B box, 2-deep), K / V blocks (192 x 128 B boxes) through a 4-stage ring in consumption order
+//            (pass A: K_0..K_n-1; pass B: K_0, V_0, K_1, V_1, ...)
+//   warp 1   MMA issuer (tcgen05.mma: S_t = Q_t K_j^T, SS, N = 192; O_t += P_t V_j, A from TMEM, B MN-major, N = 64)
+//   warp 2   TMEM allocator: query tile t owns columns [256t, 256t+256): S [0,192) / P [0,96) / O [192,256)
+//   warps 4-11  softmax + output, 4 warps per query tile, thread = query row
+#include <type_traits>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace jimm {
+
+static constexpr int ATL_THREADS = 384;
+static constexpr int ATL_KB = 192;                          // keys per block
+static constexpr int ATL_Q_BYTES = 256 * 128;               // Q pair box
+static constexpr int ATL_KV_BYTES = ATL_KB * 128;           // K or V block box
+static constexpr int ATL_NST = 4;                           // K/V ring stages
+static constexpr int ATL_SMEM = 2 * ATL_Q_BYTES + ATL_NST * ATL_KV_BYTES + 512 + 1024;
+
+struct AtlParams {
+  int B, S, H, D;
+  int n_qp;    // query pairs per (sample, head)
+  int n_blk;   // key blocks
+  float scale_log2;
+  void* out;
+};
+
+template <typename T, typename OutT>
+__global__ void __launch_bounds__(ATL_THREADS, 1)
+attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const AtlParams p) {
+  constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_q = smem;
+  uint8_t* smem_kv = smem + 2 * ATL_Q_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATL_Q_BYTES + ATL_NST * ATL_KV_BYTES);
+  uint64_t* kv_full = bars;              // [NST]
+  uint64_t* kv_empty = bars + ATL_NST;   // [NST]
+  uint64_t* q_full = bars + 2 * ATL_NST; // [2]
+  uint64_t* q_empty = q_full + 2;        // [2]
+  uint64_t* s_full = q_empty + 2;        // [2] per query tile
+  uint64_t* s_free = s_full + 2;         // [2]
+  uint64_t* p_ready = s_free + 2;        // [2]
+  uint64_t* o_full = p_ready + 2;        // [2]
+  uint64_t* o_free = o_full + 2;         // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_units = p.B * p.H * p.n_qp;
+  const int S = p.S;
+
+  pdl_launch_dependents();
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_q);
+    tma_prefetch_desc(&map_kv);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < ATL_NST; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_ready[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) tmem_alloc(tmem_ptr_smem, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t st_ph = 0;
+      int ui = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
+        const int qp = unit % p.n_qp, bh = unit / p.n_qp;
+        const int b = bh / p.H, h = bh - b * p.H;
+        const int row0 = b * S;
+        const int qb = ui & 1;
+        mbar_wait(&q_empty[qb], ((ui >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[qb], ATL_Q_BYTES);
+        tma_load_2d(smem_q + qb * ATL_Q_BYTES, &map_q, &q_full[qb], h * 64, row0 + qp * 256);
+        for (int pass = 0; pass < 2; ++pass) {
+          for (int j = 0; j < p.n_blk; ++j) {
+            for (int kv = 0; kv <= pass; ++kv) {  // pass A: K only; pass B: K then V
+              mbar_wait(&kv_empty[st], st_ph ^ 1);
+              mbar_arrive_expect_tx(&kv_full[st], ATL_KV_BYTES);
+              tma_load_2d(smem_kv + st * ATL_KV_BYTES, &map_kv, &kv_full[st], (kv + 1) * p.D + h * 64, row0 + j * ATL_KB);
+              if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc(FMT, 128, ATL_KB, 0);
+      const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);
+      int st = 0;
+      uint32_t st_ph = 0;
+      uint32_t n_sfree[2] = {0, 0}, n_pready[2] = {0, 0}, n_used[2] = {0, 0};
+      int ui = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
+        const int qp = unit % p.n_qp;
+        const int nq = (S - qp * 256 > 128) ? 2 : 1;
+        const int qb = ui & 1;
+        const uint32_t q_addr = smem_u32(smem_q + qb * ATL_Q_BYTES);
+        mbar_wait(&q_full[qb], (ui >> 1) & 1);
+        tcgen05_fence_after();
+        // ---- pass A: S blocks for the row maxima ----
+        for (int j = 0; j < p.n_blk; ++j) {
+          mbar_wait(&kv_full[st], st_ph);
+          tcgen05_fence_after();
+          const uint32_t k_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
+          for (int t = 0; t < nq; ++t) {
+            if (j > 0) { mbar_wait(&s_free[t], n_sfree[t] & 1); ++n_sfree[t]; tcgen05_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
+                         k > 0 ? 1u : 0u);
+            tcgen05_commit(&s_full[t]);
+          }
+          tcgen05_commit(&kv_empty[st]);
+          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+        }
+        // ---- pass B: S -> P -> O += P V ----
+        for (int j = 0; j < p.n_blk; ++j) {
+          mbar_wait(&kv_full[st], st_ph);
+          tcgen05_fence_after();
+          const uint32_t k_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
+          for (int t = 0; t < nq; ++t) {
+            if (j == 0) { mbar_wait(&s_free[t], n_sfree[t] & 1); ++n_sfree[t]; tcgen05_fence_after(); }  // last pass-A block was read
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
+                         k > 0 ? 1u : 0u);
+            tcgen05_commit(&s_full[t]);
+          }
+          tcgen05_commit(&kv_empty[st]);
+          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+          mbar_wait(&kv_full[st], st_ph);
+          tcgen05_fence_after();
+          const uint32_t v_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
+          for (int t = 0; t < nq; ++t) {
+            mbar_wait(&p_ready[t], n_pready[t] & 1);
+            ++n_pready[t];
+            if (j == 0 && n_used[t] > 0) mbar_wait(&o_free[t], (n_used[t] - 1) & 1);  // previous unit's O of this tile was read out
+            tcgen05_fence_after();
+#pragma unroll
+            for (int kk = 0; kk < ATL_KB / 16; ++kk)
+              umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
+                          (j | kk) != 0 ? 1u : 0u);
+            if (j == p.n_blk - 1) tcgen05_commit(&o_full[t]);
+          }
+          tcgen05_commit(&kv_empty[st]);
+          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+        }
+        tcgen05_commit(&q_empty[qb]);
+        for (int t = 0; t < nq; ++t) ++n_used[t];
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== softmax + output =====================
+    const int q = warp_idx & 3;
+    const int t = (warp_idx - 4) >> 2;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+    uint32_t n_sfull = 0, n_ofull = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      const int qp = unit % p.n_qp, bh = unit / p.n_qp;
+      const int b = bh / p.H, h = bh - b * p.H;
+      const int nq = (S - qp * 256 > 128) ? 2 : 1;
+      if (t >= nq) continue;
+      const int row = qp * 256 + t * 128 + q * 32 + lane;
+      // ---- pass A: row max over all key blocks ----
+      float m = -INFINITY;
+      uint32_t r[32], rn[32];
+      for (int j = 0; j < p.n_blk; ++j) {
+        const int kvalid = min(ATL_KB, S - j * ATL_KB);   // valid keys in this block (only the last block is partial)
+        const int n_live = (kvalid + 31) / 32, n_full = kvalid / 32;
+        mbar_wait(&s_full[t], n_sfull & 1);
+        ++n_sfull;
+        tcgen05_fence_after();
+        auto max_chunk = [&](const uint32_t (&sv)[32], int c) {
+          if (c < n_full) {
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 2) m = fmax3(m, __uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1]));
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) m = (c * 32 + jj < kvalid) ? fmaxf(m, __uint_as_float(sv[jj])) : m;
+          }
+        };
+        tmem_ld_32x32b_x32(taddr, r);
+        for (int c = 0; c < n_live; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
+          max_chunk(r, c);
+          if (c + 1 < n_live) {
+            tmem_ld_wait();
+            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
+            max_chunk(rn, c + 1);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+      }
+      // ---- pass B: P blocks (the MMA warp accumulates O) ----
+      const float moff = m * p.scale_log2;
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), mo2 = make_float2(-moff, -moff);
+      float2 l2 = make_float2(0.f, 0.f);
+      for (int j = 0; j < p.n_blk; ++j) {
+        const int kvalid = min(ATL_KB, S - j * ATL_KB);
+        const int n_live = (kvalid + 31) / 32, n_full = kvalid / 32;
+        mbar_wait(&s_full[t], n_sfull & 1);
+        ++n_sfull;
+        tcgen05_fence_after();
+        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int jj = 0; jj < 32; jj += 2) {
+            const float2 a = ffma2(make_float2(__uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1])), sc2, mo2);
+            float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            if (c >= n_full) {
+              e.x = (c * 32 + jj < kvalid) ? e.x : 0.f;
+              e.y = (c * 32 + jj + 1 < kvalid) ? e.y : 0.f;
+            }
+            l2 = fadd2(l2, e);
+            pk[jj >> 1] = pack2(e.x, e.y, FMT == 0 ? 1 : 2);
+          }
+          tmem_st_32x32b_x16(taddr + c * 16, pk);
+        };
+        tmem_ld_32x32b_x32(taddr, r);
+        for (int c = 0; c < n_live; c += 2) {
+          tmem_ld_wait();
+          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
+          softmax_chunk(r, c);
+          if (c + 1 < n_live) {
+            tmem_ld_wait();
+            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
+            softmax_chunk(rn, c + 1);
+          }
+        }
+        for (int c = n_live; c < ATL_KB / 32; ++c) {  // keys beyond S: P = 0
+          uint32_t pk[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) pk[jj] = 0u;
+          tmem_st_32x32b_x16(taddr + c * 16, pk);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[t]);
+      }
+      // ---- output ----
+      const float inv = 1.0f / (l2.x + l2.y);
+      mbar_wait(&o_full[t], n_ofull & 1);
+      ++n_ofull;
+      tcgen05_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(taddr + 192, o0);
+      tmem_ld_32x32b_x32(taddr + 224, o1);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+      if (row < S) {
+        const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64;
+        if constexpr (sizeof(OutT) == 2) {
+          uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + off);
+          constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            dst[jj] = make_uint4(pack2(__uint_as_float(o0[8 * jj]) * inv, __uint_as_float(o0[8 * jj + 1]) * inv, ot),
+                                 pack2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv, ot),
+                                 pack2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv, ot),
+                                 pack2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv, ot));
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            dst[4 + jj] = make_uint4(pack2(__uint_as_float(o1[8 * jj]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv, ot),
+                                     pack2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv, ot),
+                                     pack2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv, ot),
+                                     pack2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv, ot));
+        } else {
+          float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off);
+          constexpr bool RT = std::is_same<OutT, tf32_t>::value;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float4 v = make_float4(__uint_as_float(o0[4 * jj]) * inv, __uint_as_float(o0[4 * jj + 1]) * inv, __uint_as_float(o0[4 * jj + 2]) * inv,
+                                   __uint_as_float(o0[4 * jj + 3]) * inv);
+            if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            dst[jj] = v;
+          }
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float4 v = make_float4(__uint_as_float(o1[4 * jj]) * inv, __uint_as_float(o1[4 * jj + 1]) * inv, __uint_as_float(o1[4 * jj + 2]) * inv,
+                                   __uint_as_float(o1[4 * jj + 3]) * inv);
+            if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+            dst[8 + jj] = v;
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp_idx == 2) tmem_dealloc(tmem_base, 512);
+}
+
+int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows);  // gemm.cu
+
+template <typename T, typename OutT>
+static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int H, cudaStream_t stream) {
+  const int D = H * 64;
+  CUtensorMap map_q, map_kv;
+  if (int rc = make_tensor_map_2d(&map_q, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
+  if (int rc = make_tensor_map_2d(&map_kv, io_type, qkv, B * S, 3 * D, 3 * D, ATL_KB)) return rc;
+  AtlParams p;
+  p.B = B; p.S = S; p.H = H; p.D = D;
+  p.n_qp = (S + 255) / 256;
+  p.n_blk = (S + ATL_KB - 1) / ATL_KB;
+  p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.out = out;
+  const long long units = static_cast<long long>(B) * H * p.n_qp;
+  const int grid = units < device_sm_count() ? static_cast<int>(units) : device_sm_count();
+  static bool attr_set = false;
+  if (!attr_set) {
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_long_kernel<T, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATL_SMEM));
+    attr_set = true;
+  }
+  JIMM_CUDA_CHECK(launch_k(attention_tc_long_kernel<T, OutT>, dim3(grid), dim3(ATL_THREADS), ATL_SMEM, stream, 1, true, map_q, map_kv, p));
+  note_launch();
+  return 0;
+}
+
+// Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
+int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+  if (S <= 256 || causal) return 1;
+  if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
+  if (io_type == DT_F16 && out_type == DT_F16) return atl_launch<__half, __half>(qkv, io_type, out, B, S, H, stream);
+  if (io_type == DT_F16 && out_type == DT_F32) return atl_launch<__half, float>(qkv, io_type, out, B, S, H, stream);
+  if (io_type == DT_F16 && out_type == DT_TF32) return atl_launch<__half, tf32_t>(qkv, io_type, out, B, S, H, stream);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return atl_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, B, S, H, stream);
+  if (io_type == DT_BF16 && out_type == DT_F32) return atl_launch<__nv_bfloat16, float>(qkv, io_type, out, B, S, H, stream);
+  return 1;
+}
+
+}  // namespace jimm

@@ -50,6 +50,9 @@ int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, 
 // tcgen05 variant for S <= 256 (attention_tc.cu); returns 1 when the configuration is not handled (caller falls back).
 int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
 
+// tcgen05 two-pass variant for S > 256, non-causal (attention_tc_long.cu); returns 1 when not handled.
+int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
+
 // MAP-head attention with a single (input-independent) probe query (common/vit.py:96-97).
 //   q: fp32 [H*64] (already projected + biased), kv: [B*S, 2D] (k | v) io_type, out [B, D] out_type
 int map_attention_run(const float* q, const void* kv, int io_type, void* out, int out_type, int B, int S, int H, cudaStream_t stream);

@@ -155,7 +155,7 @@ def _attn_ref(qkv, B, S, H, causal):
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("S", [1, 16, 50, 64, 77, 128, 129, 144, 197, 200, 256, 257, 577])
+@pytest.mark.parametrize("S", [1, 16, 50, 64, 77, 128, 129, 144, 197, 200, 256, 257, 384, 385, 577, 700, 1024])
 @pytest.mark.parametrize("causal", [0, 1])
 def test_attention(lib, dtype, S, causal):
     B, H = 3, 2
@@ -169,7 +169,7 @@ def test_attention(lib, dtype, S, causal):
         assert rel_err(out, ref) < tol, (S, causal, out_dtype, rel_err(out, ref))
 
 
-@pytest.mark.parametrize("S,causal", [(130, 1), (197, 0), (256, 1)])
+@pytest.mark.parametrize("S,causal", [(130, 1), (197, 0), (256, 1), (577, 0)])
 def test_attention_flash_kernel_forced(lib, monkeypatch, S, causal):
     """S <= 256 normally takes the tcgen05 kernel; JIMM_ATTN_IMPL=flash keeps the mma.sync kernel covered there too."""
     monkeypatch.setenv("JIMM_ATTN_IMPL", "flash")
@@ -183,6 +183,15 @@ def test_attention_flash_kernel_forced(lib, monkeypatch, S, causal):
 def test_attention_many_items_persistent(lib):
     """More (sample, head) items than SMs: exercises the persistent loop, the 2-deep smem ring and TMEM slot reuse."""
     B, S, H = 40, 197, 12
+    qkv = (torch.randn(B * S, 3 * H * 64, device=DEV)).half()
+    out = torch.empty(B * S, H * 64, dtype=torch.float16, device=DEV)
+    check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F16, B, S, H, 0, stream()))
+    assert rel_err(out, _attn_ref(qkv, B, S, H, 0)) < 3e-3
+
+
+def test_attention_long_many_units_persistent(lib):
+    """S > 256: two-pass tcgen05 kernel; more units than SMs, partial last key block and single-tile last query pair."""
+    B, S, H = 24, 576, 4
     qkv = (torch.randn(B * S, 3 * H * 64, device=DEV)).half()
     out = torch.empty(B * S, H * 64, dtype=torch.float16, device=DEV)
     check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F16, B, S, H, 0, stream()))
