@@ -123,12 +123,23 @@ def build_model(workload: str, dtype_name: str):
 
 
 def cpu_threads() -> int:
-    """Threads for the CPU arm: every host core up to 32 (torch's intra-op pool stops scaling -- and then regresses -- beyond
-    that on the 128-core GPU-box hosts for this model size; JIMM_CPU_THREADS overrides)."""
+    """Threads for the CPU arm: every core this process may use (affinity mask and cgroup CPU quota honoured), capped at 32 --
+    torch's intra-op pool stops scaling, then regresses, beyond that for this model size; JIMM_CPU_THREADS overrides."""
     env = os.environ.get("JIMM_CPU_THREADS")
     if env:
         return max(1, int(env))
-    return max(1, min(os.cpu_count() or 1, 32))
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, min(n, 32))
 
 
 def oracle_step_fn(workload: str, B: int):
@@ -176,10 +187,14 @@ def time_cpu(workload: str, B: int, steps: int, warmup: int):
 
 # ----------------------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """The reference arm: the CPU restatement of the reference's forward (oracle/jimm_oracle.py, torch fp32, jimm semantics;
+    the reference's own JAX-CPU path cannot be installed in this image) on the host cores, same metric / config."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    B = args.cpu_batch
+    # bounded sample: size the per-step batch from one probe image so a step stays around 3 s of host time
+    probe_ips, _ = time_cpu(args.workload, 1, 1, 1)
+    B = args.cpu_batch if args.cpu_batch_fixed else max(1, min(16, int(probe_ips * 3.0)))
     ips, ms = time_cpu(args.workload, B, args.steps, args.warmup)
     cores = cpu_threads()
     sample = f"{B} images/step x {args.steps} steps of {WORKLOADS[args.workload][0]}"
@@ -187,7 +202,7 @@ def run_reference(args):
         "impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/sec", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": WORKLOADS[args.workload][0], "cpu_sample_batch": B},
-        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": ips, "unit": "images/sec", "cores": cores, "host_cores": os.cpu_count() or 1, "kind": "port", "sample": sample,
                          "note": "oracle/jimm_oracle.py (torch CPU fp32, jimm semantics); the reference's JAX-CPU path is not installable here"},
         "e2e": {"value": ips, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -325,6 +340,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--cpu-batch", type=int, default=4)
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-batch-fixed", action="store_true", help="reference arm: use --cpu-batch instead of sizing it from a probe")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
