@@ -4,9 +4,7 @@
 //
 // Every jimm tower with S <= 256 lands here (ViT-B/16@224: 197, SigLIP-B/16@256: 256, CLIP-B/32: 50 / 77 causal); longer
 // sequences use the flash kernel in attention.cu.  With S <= 256 a whole score row fits one TMEM accumulator, so there is
-// no online-softmax rescaling.  One persistent CTA per SM runs TWO independent item streams (item = (sample, head); stream s
-// owns smem buffer s, TMEM slot s and softmax warp group s) so that one stream's tensor-core phases (Q K^T, P V) and TMEM
-// round trips hide behind the other stream's exp2 work -- the kernel is MUFU-bound and the MUFU should never idle:
+// no online-softmax rescaling: one persistent CTA per SM loops over (sample, head) items:
 //
 //   warp 0   TMA: Q, K, V of the item (three 256 x 128 B boxes of the fused qkv buffer, SWIZZLE_128B), 2-deep ring
 //   warp 1   MMA: S_t = Q_t K^T  (tcgen05.mma SS, M=128, N=ceil16(S), K=64) for the one or two 128-row query tiles t,
@@ -80,8 +78,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
         const int b = item / p.H, h = item - b * p.H;
-        const int buf = it & 1;               // stream
-        const uint32_t ph = (it >> 1) & 1;    // this stream's item parity
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
         uint8_t* base = smem + buf * ATC_BUF_BYTES;
         mbar_wait(&kv_empty[buf], ph ^ 1);
         mbar_arrive_expect_tx(&kv_full[buf], ATC_BUF_BYTES);
@@ -92,79 +90,57 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer: an event loop multiplexing the two streams =====================
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc(FMT, 128, static_cast<uint32_t>(p.Nk), 0);
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
-      const int total_it = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
-      int it_s[2] = {0, 1};            // next item index (in this CTA's sequence) of each stream
-      int tile_s[2] = {0, 0};          // query tile inside the item
-      int need_pv[2] = {0, 0};         // 0: next op is S = Q K^T, 1: next op is O = P V
-      uint32_t n_tiles[2] = {0, 0};    // tiles issued so far per stream (parity of s_full / p_ready / o_full / slot_free)
-      bool kv_ok[2] = {false, false};
-      int live = (total_it > 0 ? 1 : 0) + (total_it > 1 ? 1 : 0);
-      bool done[2] = {total_it <= 0, total_it <= 1};
-      while (live > 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint32_t ph = (it >> 1) & 1, sp = it & 1;
+        const uint32_t q_addr = smem_u32(smem + buf * ATC_BUF_BYTES);
+        const uint32_t k_addr = q_addr + ATC_TILE_BYTES, v_addr = q_addr + 2 * ATC_TILE_BYTES;
+        mbar_wait(&kv_full[buf], ph);
+        tcgen05_fence_after();
+        for (int t = 0; t < p.nq; ++t) {
+          mbar_wait(&slot_free[t], sp ^ 1);  // the previous item's O of this tile has been read out
+          tcgen05_fence_after();
 #pragma unroll
-        for (int s2 = 0; s2 < 2; ++s2) {
-          if (done[s2]) continue;
-          const uint32_t q_addr = smem_u32(smem + s2 * ATC_BUF_BYTES);
-          const uint32_t k_addr = q_addr + ATC_TILE_BYTES, v_addr = q_addr + 2 * ATC_TILE_BYTES;
-          const uint32_t tslot = tmem_base + s2 * 256;
-          if (!need_pv[s2]) {
-            if (!kv_ok[s2]) {
-              if (!mbar_test_wait(&kv_full[s2], (it_s[s2] >> 1) & 1)) continue;
-              kv_ok[s2] = true;
-            }
-            // the previous tile's O of this slot must have been read out before S overwrites the slot
-            if (n_tiles[s2] > 0 && !mbar_test_wait(&slot_free[s2], (n_tiles[s2] - 1) & 1)) continue;
-            tcgen05_fence_after();
-            const int t = tile_s[s2];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<0>(tslot, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-            tcgen05_commit(&s_full[s2]);
-            need_pv[s2] = 1;
-          } else {
-            if (!mbar_test_wait(&p_ready[s2], n_tiles[s2] & 1)) continue;
-            tcgen05_fence_after();
-            for (int kk = 0; kk < p.Nk / 16; ++kk)
-              umma_ts_f16(tslot + 128, tslot + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv, kk > 0 ? 1u : 0u);
-            tcgen05_commit(&o_full[s2]);
-            need_pv[s2] = 0;
-            ++n_tiles[s2];
-            if (++tile_s[s2] == p.nq) {
-              tcgen05_commit(&kv_empty[s2]);  // every MMA reading this item's smem has retired
-              tile_s[s2] = 0;
-              kv_ok[s2] = false;
-              it_s[s2] += 2;
-              if (it_s[s2] >= total_it) { done[s2] = true; --live; }
-            }
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32),
+                       idesc_qk, k > 0 ? 1u : 0u);
+          tcgen05_commit(&s_full[t]);
         }
+        for (int t = 0; t < p.nq; ++t) {
+          mbar_wait(&p_ready[t], sp);
+          tcgen05_fence_after();
+          for (int kk = 0; kk < p.Nk / 16; ++kk)
+            umma_ts_f16(tmem_base + t * 256 + 128, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
+                        kk > 0 ? 1u : 0u);
+          tcgen05_commit(&o_full[t]);
+        }
+        tcgen05_commit(&kv_empty[buf]);  // every MMA reading this item's smem has retired
       }
     }
   } else if (warp_idx >= 4) {
-    // ===================== softmax + output: warp group g serves stream g =====================
-    const int q = warp_idx & 3;         // TMEM lane quarter
-    const int g = (warp_idx - 4) >> 2;  // stream
-    {
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
+    // ===================== softmax + output =====================
+    const int q = warp_idx & 3;        // TMEM lane quarter
+    const int t = (warp_idx - 4) >> 2; // query tile
+    if (t < p.nq) {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+      const int row = t * 128 + q * 32 + lane;  // query index inside the sample
       const int S = p.S;
-      const int n_chunks = (p.Nk + 31) / 32;
-      uint32_t n_tiles = 0;
-      for (int item = static_cast<int>(blockIdx.x) + g * static_cast<int>(gridDim.x); item < num_items; item += 2 * static_cast<int>(gridDim.x)) {
-       const int b = item / p.H, h = item - b * p.H;
-       for (int t = 0; t < p.nq; ++t, ++n_tiles) {
-        const int row = t * 128 + q * 32 + lane;  // query index inside the sample
-        int kmax = S;  // number of keys this row attends to
-        if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
-        // warp-uniform bounds (rows >= S are clamped: finite garbage, never stored)
-        const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
-        const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
-        const int n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
-        const uint32_t sp = n_tiles & 1;
-        mbar_wait(&s_full[g], sp);
+      int kmax = S;  // number of keys this row attends to
+      if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
+      // warp-uniform upper bound of keys any row of this warp needs (rows >= S are clamped: finite garbage, never stored)
+      const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
+      const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
+      const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
+      int it = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+        const int b = item / p.H, h = item - b * p.H;
+        const uint32_t sp = it & 1;
+        mbar_wait(&s_full[t], sp);
         tcgen05_fence_after();
         // ---- pass 1: row max (next chunk's TMEM load in flight while this one is reduced) ----
         // Chunks below n_full hold only valid keys for every lane of the warp: no per-element masking there.
@@ -244,10 +220,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[g]);
+        if (lane == 0) mbar_arrive(&p_ready[t]);
         // ---- output: O / l ----
         const float inv = 1.0f / l;
-        mbar_wait(&o_full[g], sp);
+        mbar_wait(&o_full[t], sp);
         tcgen05_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32b_x32(taddr + 128, o0);
@@ -255,7 +231,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[g]);  // this slot may now be overwritten by the next tile's S
+        if (lane == 0) mbar_arrive(&slot_free[t]);  // TMEM of this tile may be overwritten by the next item's S
         if (row < S) {
           const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64;
           if constexpr (sizeof(OutT) == 2) {
@@ -292,8 +268,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
             }
           }
         }
-       }  // tile
-      }    // item
+      }
     }
   }
 
@@ -335,7 +310,7 @@ static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int
 int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
   // One query tile (S <= 128) leaves half of the softmax warps idle: the flash kernel is as fast or faster there (measured:
   // S=50 39 us vs 25 us, S=77 causal 35 vs 37 us; S=197 128 vs 218 us, S=256 140 vs 215 us at B=256).
-  if (S > 256 || S < 1) return 1;
+  if (S > 256 || S <= 128) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
   if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, B, S, H, causal, stream);
   if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, B, S, H, causal, stream);
