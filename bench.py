@@ -305,10 +305,13 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cb = args.cpu_batch
-        ips, _ = time_cpu(args.workload, cb, args.cpu_steps, 1)
+        # bounded sample of the same workload: ~12 s of host time, sized from a one-image probe
+        probe_ips, _ = time_cpu(args.workload, 1, 1, 1)
+        cb = max(1, min(16, int(probe_ips * 2.0)))
+        csteps = args.cpu_steps if args.cpu_steps > 0 else max(2, min(60, int(12.0 * probe_ips / cb)))
+        ips, _ = time_cpu(args.workload, cb, csteps, 1)
         cpu = {"value": ips, "unit": "images/sec", "cores": cpu_threads(), "host_cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"{cb} images/step x {args.cpu_steps} steps, oracle/jimm_oracle.py torch-CPU fp32 (jimm semantics)"}
+               "sample": f"{cb} images/step x {csteps} steps, oracle/jimm_oracle.py torch-CPU fp32 (jimm semantics)"}
 
     if rank == 0:
         gflop = GFLOP_PER_IMG[args.workload]
@@ -339,7 +342,7 @@ def main():
     ap.add_argument("--workload", default="vit_b16", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--cpu-batch", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=0, help="0 = size the CPU sample for ~12 s")
     ap.add_argument("--cpu-batch-fixed", action="store_true", help="reference arm: use --cpu-batch instead of sizing it from a probe")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -180,6 +180,81 @@ def test_tower_map_pooling():
     assert rel(out, ref) < TOL, rel(out, ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_tower_map_pooling_other_dtypes(dtype):
+    """MAP tower in bf16 (vs the same-rounding oracle) and fp32/tf32 mode (vs the fp32 oracle)."""
+    from jimm_b200.common.vit import VisionTransformerBase
+
+    t = O.TowerCfg(img_size=64, patch_size=16, in_channels=3, hidden_size=256, num_layers=2, num_heads=4, mlp_dim=1024,
+                   pooling_type="MAP", layernorm_epsilon=1e-6)
+    p = O.random_tower_params(t, seed=3)
+    img = O.synthetic_images(5, 64)
+    with torch.no_grad():
+        ref = O.vision_tower(p, "", img, t)
+        ref_same = O.vision_tower(p, "", img, t, O.Semantics(operand_round="bf16")) if dtype == torch.bfloat16 else ref
+    m = _set(VisionTransformerBase(img_size=64, patch_size=16, in_channels=3, hidden_size=256, num_layers=2, num_heads=4, mlp_dim=1024,
+                                   pooling_type="MAP", layernorm_epsilon=1e-6, dtype=dtype), p)
+    out = m(img.cuda())
+    if dtype == torch.float32:
+        assert rel(out, ref) < TOL, rel(out, ref)
+    else:
+        assert rel(out, ref_same) < 8e-3 and rel(out, ref) < 1.5e-2, (rel(out, ref_same), rel(out, ref))
+
+
+def test_config3_shape_vit_l16_384_map_bf16_reduced_depth():
+    """BASELINE config 3 shapes (ViT-L/16 @384, MAP head, bf16; S = 576 -> two-pass tcgen05 attention) with 2 of the 24 layers."""
+    from jimm_b200.common.vit import VisionTransformerBase
+
+    t = O.TowerCfg(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=2, num_heads=16, mlp_dim=4096,
+                   pooling_type="MAP", layernorm_epsilon=1e-6)
+    p = O.random_tower_params(t, seed=5)
+    img = O.synthetic_images(3, 384)
+    with torch.no_grad():
+        ref = O.vision_tower(p, "", img, t)
+        ref_same = O.vision_tower(p, "", img, t, O.Semantics(operand_round="bf16"))
+    m = _set(VisionTransformerBase(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=2, num_heads=16, mlp_dim=4096,
+                                   pooling_type="MAP", layernorm_epsilon=1e-6, dtype=torch.bfloat16), p)
+    out = m(img.cuda())
+    assert out.shape == (3, 1024)
+    assert rel(out, ref_same) < 8e-3 and rel(out, ref) < 1.5e-2, (rel(out, ref_same), rel(out, ref))
+    m16 = _set(VisionTransformerBase(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=2, num_heads=16, mlp_dim=4096,
+                                     pooling_type="MAP", layernorm_epsilon=1e-6, dtype=torch.float16), p)
+    assert rel(m16(img.cuda()), ref) < TOL
+
+
+def test_config4_shape_clip_b32_reduced_depth():
+    """BASELINE config 4 shapes (CLIP ViT-B/32: vision 768/P32@224, text 512/8H/T77/V49408, E=512) with 2 layers per tower."""
+    from jimm_b200.models import CLIP
+
+    cfg = O.DualCfg(224, 2, 768, 32, 77, 49408, 512, 8, 2)
+    p = O.random_dual_params(cfg, "clip", seed=7)
+    img, txt = O.synthetic_images(5, 224), O.synthetic_tokens(7, 77, 49408, "clip")
+    with torch.no_grad():
+        ref = O.clip_forward(p, cfg, img, txt)
+    m = _set(CLIP(224, 2, 768, 32, 77, 49408, 512, 8, 2, dtype=torch.float16), p)
+    out = m(img.cuda(), txt.cuda())
+    assert out.shape == (5, 7)
+    assert rel(out, ref) < TOL, rel(out, ref)
+    assert torch.equal(out.argmax(-1).cpu(), ref.argmax(-1))
+
+
+def test_config5_shape_siglip2_l16_512_reduced_depth():
+    """BASELINE config 5 shapes (SigLIP2-L/16 @512: vision 1024/16H, S = 1024; text 1024/16H/T64) with 2 layers per tower and
+    a reduced vocabulary (the gather cost is vocabulary independent)."""
+    from jimm_b200.models import SigLIP
+
+    cfg = O.DualCfg(512, 2, 1024, 16, 64, 4096, 1024, 16, 2)
+    p = O.random_dual_params(cfg, "siglip", seed=9)
+    img, txt = O.synthetic_images(2, 512), O.synthetic_tokens(3, 64, 4096, "siglip")
+    with torch.no_grad():
+        ref_i = O.siglip_encode_image(p, cfg, img)
+        ref = O.siglip_forward(p, cfg, img, txt)
+    m = _set(SigLIP(512, 2, 1024, 16, 64, 4096, 1024, 16, 2, dtype=torch.float16), p)
+    assert rel(m.encode_image(img.cuda()), ref_i) < TOL
+    out = m(img.cuda(), txt.cuda())
+    assert rel(out, ref) < 2e-3, rel(out, ref)
+
+
 @pytest.mark.parametrize("kind", ["clip", "siglip"])
 def test_dual_tower_medium(kind):
     from jimm_b200.models import CLIP, SigLIP
