@@ -13,7 +13,7 @@
 //            the first N/2 columns, O in columns 128..191)
 //   warps 4-11  softmax + output, one group of 4 warps per query tile, thread = query row: pass 1 row max from TMEM,
 //            pass 2 exp2 / row sum / pack / tcgen05.st P, then O * (1/l) -> global after the P V MMA.
-// The kernel is MUFU(exp2)-bound by construction (S^2 exponentials per head vs 4 S^2 64 MACs on the tensor pipe).
+// Measured bound: TMEM read bandwidth (~64 B/clk/SM), hence the single pass over S with a lazily raised reference maximum.
 #include <type_traits>
 
 #include "common.cuh"
@@ -25,6 +25,18 @@ static constexpr int ATC_THREADS = 384;
 static constexpr int ATC_TILE_BYTES = 256 * 128;                 // one Q / K / V box
 static constexpr int ATC_BUF_BYTES = 3 * ATC_TILE_BYTES;          // 96 KB per item
 static constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 256 + 1024;
+
+// multiply a packed pair of 16-bit values by f (rare lazy-rescale path)
+template <typename T>
+__device__ __forceinline__ uint32_t scale_pair(uint32_t v, float f) {
+  if constexpr (std::is_same<T, __half>::value) {
+    const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&v), __float2half2_rn(f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  } else {
+    const __nv_bfloat162 h = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&v), __float2bfloat162_rn(f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+}
 
 struct AtcParams {
   int B, S, H, D;
@@ -142,41 +154,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         const uint32_t sp = it & 1;
         mbar_wait(&s_full[t], sp);
         tcgen05_fence_after();
-        // ---- pass 1: row max (next chunk's TMEM load in flight while this one is reduced) ----
-        // Chunks below n_full hold only valid keys for every lane of the warp: no per-element masking there.
-        float m = -INFINITY;
+        // ---- single pass over S (the kernel is bound by TMEM read bandwidth, ~64 B/clk/SM: reading the scores twice for an
+        //      exact row max first cost 45 % more; profiles/r1_d).  Lazy-rescale softmax: p = exp2((s - m_ref) * scale) against a
+        //      reference maximum that is only raised when a chunk's maximum exceeds it by more than 2^8 in the exp2 domain (so
+        //      p <= 256, far inside fp16/bf16 range); the rare raise rescales the row sum and the P chunks already written. ----
+        float m_ref = -INFINITY;
+        float2 l2 = make_float2(0.f, 0.f);
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+        const float th_raw = 8.0f / p.scale_log2;
         uint32_t r[32], rn[32];
-        auto max_chunk = [&](const uint32_t (&sv)[32], int c) {
+        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
+          // chunk maximum over this row's valid keys
+          float cm = -INFINITY;
           if (c < n_full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) m = fmax3(m, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+            for (int j = 0; j < 32; j += 2) cm = fmax3(cm, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float v = __uint_as_float(sv[j]);
-              m = (c * 32 + j < kmax) ? fmaxf(m, v) : m;
+            for (int j = 0; j < 32; ++j) cm = (c * 32 + j < kmax) ? fmaxf(cm, __uint_as_float(sv[j])) : cm;
+          }
+          const bool raise = cm > m_ref + th_raw;  // always true for the first valid chunk (m_ref = -inf)
+          if (__any_sync(0xffffffffu, raise)) {
+            const float new_ref = raise ? cm : m_ref;
+            const float f = raise ? ex2_approx((m_ref - new_ref) * p.scale_log2) : 1.0f;  // exp2(-inf) = 0 on the first chunk
+            l2.x *= f;
+            l2.y *= f;
+            m_ref = new_ref;
+            if (c > 0) {  // rescale the P chunks already stored (rare)
+              tmem_st_wait();
+              for (int j = 0; j < c; ++j) {
+                uint32_t pp[16];
+                tmem_ld_32x32b_x16(taddr + j * 16, pp);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pp[e] = scale_pair<T>(pp[e], f);
+                tmem_st_32x32b_x16(taddr + j * 16, pp);
+              }
             }
           }
-        };
-        tmem_ld_32x32b_x32(taddr, r);
-        for (int c = 0; c < n_live; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
-          max_chunk(r, c);
-          if (c + 1 < n_live) {
-            tmem_ld_wait();
-            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
-            max_chunk(rn, c + 1);
-          }
-        }
-        const float moff = m * p.scale_log2;
-        // ---- pass 2: p = exp2(s * scale - max), row sum, P (16-bit) back into TMEM over the consumed S columns ----
-        // P chunk c (16 columns) lands on S columns [16c, 16c+16) which belong to S chunk c/2 <= c: already in registers.
-        // With the one-chunk-ahead prefetch S chunk c+1 is read BEFORE P chunk c is stored, and 16(c)+16 <= 32(c+1), so the
-        // store never clobbers a chunk that has not been loaded yet.
-        float2 l2 = make_float2(0.f, 0.f);
-        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), mo2 = make_float2(-moff, -moff);
-        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
+          const float2 mo2 = make_float2(-m_ref * p.scale_log2, -m_ref * p.scale_log2);
           uint32_t pk[16];
           if (c < n_full) {
 #pragma unroll
@@ -199,6 +215,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
           }
           tmem_st_32x32b_x16(taddr + c * 16, pk);
         };
+        // P chunk c (16 columns) lands on S columns [16c, 16c+16), inside S chunk c/2 <= c, which is already in registers; the
+        // one-chunk-ahead prefetch reads S chunk c+1 BEFORE P chunk c is stored and 16c+16 <= 32(c+1).
         tmem_ld_32x32b_x32(taddr, r);
         for (int c = 0; c < n_live; c += 2) {
           tmem_ld_wait();

@@ -198,8 +198,28 @@ def test_attention_long_many_units_persistent(lib):
     assert rel_err(out, _attn_ref(qkv, B, S, H, 0)) < 3e-3
 
 
+@pytest.mark.parametrize("S", [197, 256])
+def test_attention_lazy_rescale_path(lib, S):
+    """Scores that keep growing along the key axis force the lazily raised reference maximum (and the rescale of the P chunks
+    already written to tensor memory) at every 32-key chunk of the single-pass softmax."""
+    B, H = 2, 2
+    g = torch.Generator(device="cpu").manual_seed(3)
+    q = torch.randn(B, S, H, 64, generator=g)
+    ramp = torch.linspace(0.0, 40.0, S).reshape(1, S, 1, 1)  # key j gets a bias direction scaled by j
+    u = torch.nn.functional.normalize(torch.randn(1, 1, H, 64, generator=g), dim=-1)
+    k = torch.randn(B, S, H, 64, generator=g) * 0.3 + ramp * u * 3.0
+    q = q * 0.3 + u * 8.0
+    v = torch.randn(B, S, H, 64, generator=g)
+    qkv = torch.stack([q, k, v], dim=2).reshape(B * S, 3 * H * 64).to(DEV).half()
+    out = torch.empty(B * S, H * 64, dtype=torch.float32, device=DEV)
+    check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F32, B, S, H, 0, stream()))
+    ref = _attn_ref(qkv, B, S, H, 0)
+    assert torch.isfinite(out).all()
+    assert rel_err(out, ref) < 5e-3, rel_err(out, ref)
+
+
 def test_attention_large_scores_stable(lib):
-    B, S, H = 1, 130, 1
+    B, S, H = 1, 230, 1
     qkv = (torch.randn(B * S, 3 * 64, device=DEV) * 12).half()
     out = torch.empty(B * S, 64, dtype=torch.float32, device=DEV)
     check(lib, lib.jimm_k_attention(ptr(qkv), F16, ptr(out), F32, B, S, H, 0, stream()))
