@@ -24,7 +24,8 @@ namespace jimm {
 static constexpr int ATC_THREADS = 384;
 static constexpr int ATC_TILE_BYTES = 256 * 128;                 // one Q / K / V box
 static constexpr int ATC_BUF_BYTES = 3 * ATC_TILE_BYTES;          // 96 KB per item
-static constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + 256 + 1024;
+static constexpr int ATC_OBUF_BYTES = 8 * 32 * 128;                // one 32 x 128 B store box per softmax warp
+static constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + ATC_OBUF_BYTES + 256 + 1024;
 
 // multiply a packed pair of 16-bit values by f (rare lazy-rescale path)
 template <typename T>
@@ -48,11 +49,12 @@ struct AtcParams {
 
 template <typename T, typename OutT, bool CAUSAL>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const AtcParams p) {
   constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATC_BUF_BYTES);
+  uint8_t* obuf_base = smem + 2 * ATC_BUF_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATC_BUF_BYTES + ATC_OBUF_BYTES);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
   uint64_t* s_full = bars + 4;     // [2] per query tile
@@ -65,7 +67,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
   const int num_items = p.B * p.H;
 
   pdl_launch_dependents();
-  if (warp_idx == 0 && lane == 0) tma_prefetch_desc(&map_qkv);
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_out);
+  }
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
@@ -140,6 +145,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
     const int t = (warp_idx - 4) >> 2; // query tile
     if (t < p.nq) {
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+      uint8_t* obuf = obuf_base + (warp_idx - 4) * (32 * 128);
       const int row = t * 128 + q * 32 + lane;  // query index inside the sample
       const int S = p.S;
       int kmax = S;  // number of keys this row attends to
@@ -215,17 +221,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
           }
           tmem_st_32x32b_x16(taddr + c * 16, pk);
         };
-        // P chunk c (16 columns) lands on S columns [16c, 16c+16), inside S chunk c/2 <= c, which is already in registers; the
-        // one-chunk-ahead prefetch reads S chunk c+1 BEFORE P chunk c is stored and 16c+16 <= 32(c+1).
+        // P chunk c (16 columns) lands on S columns [16c, 16c+16), inside S chunk c/2 <= c, which is already in registers; S
+        // chunks c+1 .. c+3 that may be in flight start at column 32(c+1) >= 16c+16.
+        // two x32 loads per tcgen05.wait::ld (the wait is a MEMBAR-class instruction: halve their number); a buffer is refilled
+        // as soon as its chunk has been consumed, so the loads of chunks c+2 / c+3 fly during the math of chunks c / c+1
         tmem_ld_32x32b_x32(taddr, r);
+        if (n_live > 1) tmem_ld_32x32b_x32(taddr + 32, rn);
         for (int c = 0; c < n_live; c += 2) {
           tmem_ld_wait();
-          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
           softmax_chunk(r, c);
+          if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
           if (c + 1 < n_live) {
-            tmem_ld_wait();
-            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
             softmax_chunk(rn, c + 1);
+            if (c + 3 < n_live) tmem_ld_32x32b_x32(taddr + (c + 3) * 32, rn);
           }
         }
         const float l = l2.x + l2.y;
@@ -250,39 +258,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&slot_free[t]);  // TMEM of this tile may be overwritten by the next item's S
-        if (row < S) {
-          const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64;
-          if constexpr (sizeof(OutT) == 2) {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + off);
-            constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
+        // O tile rows -> swizzled 32 x 128 B box in smem -> 3-D TMA store (rows >= S are clipped by the [B, S, D] tensor map;
+        // the row-per-thread 16-byte global stores this replaces cost 32 LSU wavefronts per instruction)
+        {
+          constexpr int NBOX = sizeof(OutT) == 2 ? 1 : 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack2(__uint_as_float(o0[8 * j]) * inv, __uint_as_float(o0[8 * j + 1]) * inv, ot),
-                                  pack2(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv, ot),
-                                  pack2(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv, ot),
-                                  pack2(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv, ot));
+          for (int bx = 0; bx < NBOX; ++bx) {
+            uint32_t pk[32];
+            if constexpr (sizeof(OutT) == 2) {
+              constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[4 + j] = make_uint4(pack2(__uint_as_float(o1[8 * j]) * inv, __uint_as_float(o1[8 * j + 1]) * inv, ot),
-                                      pack2(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv, ot),
-                                      pack2(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv, ot),
-                                      pack2(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv, ot));
-          } else {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off);
-            constexpr bool RT = std::is_same<OutT, tf32_t>::value;
+              for (int j = 0; j < 16; ++j) {
+                pk[j] = pack2(__uint_as_float(o0[2 * j]) * inv, __uint_as_float(o0[2 * j + 1]) * inv, ot);
+                pk[16 + j] = pack2(__uint_as_float(o1[2 * j]) * inv, __uint_as_float(o1[2 * j + 1]) * inv, ot);
+              }
+            } else {
+              constexpr bool RT = std::is_same<OutT, tf32_t>::value;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 v = make_float4(__uint_as_float(o0[4 * j]) * inv, __uint_as_float(o0[4 * j + 1]) * inv,
-                                     __uint_as_float(o0[4 * j + 2]) * inv, __uint_as_float(o0[4 * j + 3]) * inv);
-              if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-              dst[j] = v;
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(bx == 0 ? o0[j] : o1[j]) * inv;
+                pk[j] = __float_as_uint(RT ? round_tf32(v) : v);
+              }
             }
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 v = make_float4(__uint_as_float(o1[4 * j]) * inv, __uint_as_float(o1[4 * j + 1]) * inv,
-                                     __uint_as_float(o1[4 * j + 2]) * inv, __uint_as_float(o1[4 * j + 3]) * inv);
-              if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-              dst[8 + j] = v;
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(obuf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_out, smem_u32(obuf), h * 64 + bx * 32, t * 128 + q * 32, b);
+              tma_store_commit();
             }
           }
         }
@@ -290,6 +297,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
     }
   }
 
+  if (warp_idx >= 4 && lane == 0) tma_store_wait_all();
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -298,12 +306,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const AtcParams
 
 // ---- host ----------------------------------------------------------------------------------------------------------
 int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows);  // gemm.cu
+int make_tensor_map_3d(CUtensorMap* map, int dtype, const void* ptr, int B, int S, int N, int ld);              // gemm.cu
 
 template <typename T, typename OutT>
-static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int H, int causal, cudaStream_t stream) {
+static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
   const int D = H * 64;
   CUtensorMap map;
   if (int rc = make_tensor_map_2d(&map, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
+  CUtensorMap map_out;
+  if (int rc = make_tensor_map_3d(&map_out, out_type, out, B, S, D, D)) return rc;
   AtcParams p;
   p.B = B; p.S = S; p.H = H; p.D = D;
   p.nq = (S + 127) / 128;
@@ -318,8 +329,8 @@ static int atc_launch(const void* qkv, int io_type, void* out, int B, int S, int
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
     attr_set = true;
   }
-  if (causal) JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, p));
-  else JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, p));
+  if (causal) JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, map_out, p));
+  else JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, map_out, p));
   note_launch();
   return 0;
 }
@@ -330,11 +341,11 @@ int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int 
   // S=50 39 us vs 25 us, S=77 causal 35 vs 37 us; S=197 128 vs 218 us, S=256 140 vs 215 us at B=256).
   if (S > 256 || S <= 128) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
-  if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_TF32) return atc_launch<__half, tf32_t>(qkv, io_type, out, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_BF16) return atc_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_F32) return atc_launch<__nv_bfloat16, float>(qkv, io_type, out, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, out_type, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, out_type, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_TF32) return atc_launch<__half, tf32_t>(qkv, io_type, out, out_type, B, S, H, causal, stream);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return atc_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, out_type, B, S, H, causal, stream);
+  if (io_type == DT_BF16 && out_type == DT_F32) return atc_launch<__nv_bfloat16, float>(qkv, io_type, out, out_type, B, S, H, causal, stream);
   return 1;
 }
 

@@ -559,19 +559,24 @@ static int make_map(CUtensorMap* map, int dtype, const void* ptr, int rows, int 
   return 0;
 }
 
-// 3-D fp32 tensor map over out[B, S, N] (dims {N, S, B}), box {32 cols, 32 rows, 1}, SWIZZLE_128B
-static int make_map_3d_f32(CUtensorMap* map, const void* ptr, int B, int S, int N, int ld) {
+// 3-D tensor map over out[B, S, N] (dims {N, S, B}), box {128 B of columns, 32 rows, 1}, SWIZZLE_128B: rows >= S are clipped,
+// so a 32-row box never spills into the next sample.
+int make_tensor_map_3d(CUtensorMap* map, int dtype, const void* ptr, int B, int S, int N, int ld) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return -3;
+  const size_t es = dtype_size(dtype);
+  CUtensorMapDataType dt = (dtype == DT_F32 || dtype == DT_TF32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
   cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * 4, static_cast<cuuint64_t>(S) * ld * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(S) * ld * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(128 / es), 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", static_cast<int>(r)); return -3; }
   return 0;
 }
+static int make_map_3d_f32(CUtensorMap* map, const void* ptr, int B, int S, int N, int ld) { return make_tensor_map_3d(map, DT_F32, ptr, B, S, N, ld); }
 
 int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows) {
   return make_map(map, dtype, ptr, rows, cols, ld, box_rows);
