@@ -75,10 +75,10 @@ __device__ __forceinline__ void load_tile(uint32_t smem_base, const T* __restric
 
 template <typename T, typename OutT, bool CAUSAL>
 __global__ void __launch_bounds__(128)
-attention_kernel(const T* __restrict__ qkv, OutT* __restrict__ out, int S, int H, float scale_log2) {
+attention_kernel(const T* __restrict__ qkv, OutT* __restrict__ out, int S, int H, float scale_log2, int reverse) {
   __shared__ __align__(128) uint8_t smem[QT * 128 + 2 * 2 * KT * 128];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x, h = blockIdx.y, b = reverse ? static_cast<int>(gridDim.z) - 1 - static_cast<int>(blockIdx.z) : static_cast<int>(blockIdx.z);
   const int D = H * HD;
   const size_t ld = static_cast<size_t>(3) * D;
   const T* base = qkv + static_cast<size_t>(b) * S * ld + h * HD;
@@ -265,30 +265,30 @@ attention_kernel(const T* __restrict__ qkv, OutT* __restrict__ out, int S, int H
 }
 
 template <typename T, typename OutT>
-static int attn_launch(const void* qkv, void* out, int B, int S, int H, int causal, cudaStream_t stream) {
+static int attn_launch(const void* qkv, void* out, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   dim3 grid((S + QT - 1) / QT, H, B);
   const float scale_log2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)
-  if (causal) JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, true>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2));
-  else JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, false>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2));
+  if (causal) JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, true>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2, reverse));
+  else JIMM_CUDA_CHECK(launch_k(attention_kernel<T, OutT, false>, grid, dim3(128), 0, stream, 1, true, static_cast<const T*>(qkv), static_cast<OutT*>(out), S, H, scale_log2, reverse));
   note_launch();
   return 0;
 }
 
-int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   if (B <= 0 || S <= 0) return 0;
   const char* env = getenv("JIMM_ATTN_IMPL");  // "flash" forces the mma.sync flash kernel (A/B comparison, bisection)
   if (!(env && strcmp(env, "flash") == 0)) {
-    int rc = attention_tc_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
+    int rc = attention_tc_run(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
     if (rc <= 0) return rc;
-    rc = attention_tc_long_run(qkv, io_type, out, out_type, B, S, H, causal, stream);
+    rc = attention_tc_long_run(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
     if (rc <= 0) return rc;
   }
   if (B > 65535 || H > 65535) { set_last_error("attention: grid too large (B=%d H=%d)", B, H); return -1; }
-  if (io_type == DT_F16 && out_type == DT_F16) return attn_launch<__half, __half>(qkv, out, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_F32) return attn_launch<__half, float>(qkv, out, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_TF32) return attn_launch<__half, tf32_t>(qkv, out, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_BF16) return attn_launch<__nv_bfloat16, __nv_bfloat16>(qkv, out, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_F32) return attn_launch<__nv_bfloat16, float>(qkv, out, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_F16) return attn_launch<__half, __half>(qkv, out, B, S, H, causal, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_F32) return attn_launch<__half, float>(qkv, out, B, S, H, causal, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_TF32) return attn_launch<__half, tf32_t>(qkv, out, B, S, H, causal, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return attn_launch<__nv_bfloat16, __nv_bfloat16>(qkv, out, B, S, H, causal, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_F32) return attn_launch<__nv_bfloat16, float>(qkv, out, B, S, H, causal, stream, reverse);
   set_last_error("attention: unsupported dtype combination io=%d out=%d", io_type, out_type);
   return -1;
 }

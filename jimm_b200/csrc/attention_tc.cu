@@ -45,6 +45,7 @@ struct AtcParams {
   int Nk;       // keys rounded up to 16 (MMA N of S = Q K^T, MMA K of O = P V)
   float scale_log2;
   void* out;
+  int reverse;  // walk the (sample, head) items from the end (see kernels.cuh)
 };
 
 template <typename T, typename OutT, bool CAUSAL>
@@ -94,7 +95,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     if (lane == 0) {
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int b = item / p.H, h = item - b * p.H;
+        const int ie = p.reverse ? num_items - 1 - item : item;
+        const int b = ie / p.H, h = ie - b * p.H;
         const int buf = it & 1;
         const uint32_t ph = (it >> 1) & 1;
         uint8_t* base = smem + buf * ATC_BUF_BYTES;
@@ -156,7 +158,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
       int it = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int b = item / p.H, h = item - b * p.H;
+        const int ie = p.reverse ? num_items - 1 - item : item;
+        const int b = ie / p.H, h = ie - b * p.H;
         const uint32_t sp = it & 1;
         mbar_wait(&s_full[t], sp);
         tcgen05_fence_after();
@@ -309,7 +312,7 @@ int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, i
 int make_tensor_map_3d(CUtensorMap* map, int dtype, const void* ptr, int B, int S, int N, int ld);              // gemm.cu
 
 template <typename T, typename OutT>
-static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   const int D = H * 64;
   CUtensorMap map;
   if (int rc = make_tensor_map_2d(&map, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
@@ -321,6 +324,7 @@ static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int
   p.Nk = ((S + 15) / 16) * 16;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = out;
+  p.reverse = reverse;
   const int items = B * H;
   const int grid = items < device_sm_count() ? items : device_sm_count();
   static bool attr_set = false;
@@ -336,16 +340,16 @@ static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int
 }
 
 // Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
-int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   // One query tile (S <= 128) leaves half of the softmax warps idle: the flash kernel is as fast or faster there (measured:
   // S=50 39 us vs 25 us, S=77 causal 35 vs 37 us; S=197 128 vs 218 us, S=256 140 vs 215 us at B=256).
   if (S > 256 || S <= 128) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
-  if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, out_type, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, out_type, B, S, H, causal, stream);
-  if (io_type == DT_F16 && out_type == DT_TF32) return atc_launch<__half, tf32_t>(qkv, io_type, out, out_type, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_BF16) return atc_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, out_type, B, S, H, causal, stream);
-  if (io_type == DT_BF16 && out_type == DT_F32) return atc_launch<__nv_bfloat16, float>(qkv, io_type, out, out_type, B, S, H, causal, stream);
+  if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_TF32) return atc_launch<__half, tf32_t>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return atc_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_F32) return atc_launch<__nv_bfloat16, float>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
   return 1;
 }
 

@@ -32,6 +32,7 @@ struct AtlParams {
   int n_blk;   // key blocks
   float scale_log2;
   void* out;
+  int reverse;
 };
 
 template <typename T, typename OutT>
@@ -93,7 +94,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       uint32_t st_ph = 0;
       int ui = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
-        const int qp = unit % p.n_qp, bh = unit / p.n_qp;
+        const int ue = p.reverse ? num_units - 1 - unit : unit;
+        const int qp = ue % p.n_qp, bh = ue / p.n_qp;
         const int b = bh / p.H, h = bh - b * p.H;
         const int row0 = b * S;
         const int qb = ui & 1;
@@ -122,7 +124,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       uint32_t n_sfree[2] = {0, 0}, n_pready[2] = {0, 0}, n_used[2] = {0, 0};
       int ui = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
-        const int qp = unit % p.n_qp;
+        const int ue = p.reverse ? num_units - 1 - unit : unit;
+        const int qp = ue % p.n_qp;
         const int nq = (S - qp * 256 > 128) ? 2 : 1;
         const int qb = ui & 1;
         const uint32_t q_addr = smem_u32(smem_q + qb * ATL_Q_BYTES);
@@ -187,7 +190,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
     uint32_t n_sfull = 0, n_ofull = 0;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
-      const int qp = unit % p.n_qp, bh = unit / p.n_qp;
+      const int ue = p.reverse ? num_units - 1 - unit : unit;
+      const int qp = ue % p.n_qp, bh = ue / p.n_qp;
       const int b = bh / p.H, h = bh - b * p.H;
       const int nq = (S - qp * 256 > 128) ? 2 : 1;
       if (t >= nq) continue;
@@ -332,7 +336,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, int cols, int ld, int box_rows);  // gemm.cu
 
 template <typename T, typename OutT>
-static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int H, cudaStream_t stream) {
+static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int H, cudaStream_t stream, int reverse) {
   const int D = H * 64;
   CUtensorMap map_q, map_kv;
   if (int rc = make_tensor_map_2d(&map_q, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
@@ -343,6 +347,7 @@ static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int
   p.n_blk = (S + ATL_KB - 1) / ATL_KB;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = out;
+  p.reverse = reverse;
   const long long units = static_cast<long long>(B) * H * p.n_qp;
   const int grid = units < device_sm_count() ? static_cast<int>(units) : device_sm_count();
   static bool attr_set = false;
@@ -356,14 +361,14 @@ static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int
 }
 
 // Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
-int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream) {
+int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   if (S <= 256 || causal) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
-  if (io_type == DT_F16 && out_type == DT_F16) return atl_launch<__half, __half>(qkv, io_type, out, B, S, H, stream);
-  if (io_type == DT_F16 && out_type == DT_F32) return atl_launch<__half, float>(qkv, io_type, out, B, S, H, stream);
-  if (io_type == DT_F16 && out_type == DT_TF32) return atl_launch<__half, tf32_t>(qkv, io_type, out, B, S, H, stream);
-  if (io_type == DT_BF16 && out_type == DT_BF16) return atl_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, B, S, H, stream);
-  if (io_type == DT_BF16 && out_type == DT_F32) return atl_launch<__nv_bfloat16, float>(qkv, io_type, out, B, S, H, stream);
+  if (io_type == DT_F16 && out_type == DT_F16) return atl_launch<__half, __half>(qkv, io_type, out, B, S, H, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_F32) return atl_launch<__half, float>(qkv, io_type, out, B, S, H, stream, reverse);
+  if (io_type == DT_F16 && out_type == DT_TF32) return atl_launch<__half, tf32_t>(qkv, io_type, out, B, S, H, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_BF16) return atl_launch<__nv_bfloat16, __nv_bfloat16>(qkv, io_type, out, B, S, H, stream, reverse);
+  if (io_type == DT_BF16 && out_type == DT_F32) return atl_launch<__nv_bfloat16, float>(qkv, io_type, out, B, S, H, stream, reverse);
   return 1;
 }
 

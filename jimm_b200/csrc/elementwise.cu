@@ -18,12 +18,13 @@ template <typename OutT, int MAXV>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, size_t ldx, int group, int row_off, const int* __restrict__ row_index,
                  const float* __restrict__ scale, const float* __restrict__ bias, float eps, OutT* __restrict__ out, size_t ldy,
-                 int rows, int D) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                 int rows, int D, int reverse) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   pdl_launch_dependents();
   pdl_wait();
   if (warp >= rows) return;
+  if (reverse) warp = rows - 1 - warp;
   const size_t src_row = static_cast<size_t>(warp) * group + (row_index ? row_index[warp] : row_off);
   const float4* xr = reinterpret_cast<const float4*>(x + src_row * ldx);
   const int nv = D >> 2;
@@ -74,31 +75,31 @@ layernorm_kernel(const float* __restrict__ x, size_t ldx, int group, int row_off
 
 template <typename OutT>
 static int ln_launch(const float* x, int ldx, int group, int row_off, const int* row_index, const float* scale, const float* bias,
-                     float eps, void* out, int ldy, int rows, int D, cudaStream_t stream) {
+                     float eps, void* out, int ldy, int rows, int D, cudaStream_t stream, int reverse) {
   const int threads = 256, wpb = threads / 32;
   const int grid = (rows + wpb - 1) / wpb;
   const int nv = D / 4;
   if (nv <= 32 * 8)
     JIMM_CUDA_CHECK(launch_k(layernorm_kernel<OutT, 8>, dim3(grid), dim3(threads), 0, stream, 1, true, x, ldx, group, row_off, row_index, scale, bias, eps,
-                             static_cast<OutT*>(out), ldy, rows, D));
+                             static_cast<OutT*>(out), ldy, rows, D, reverse));
   else
     JIMM_CUDA_CHECK(launch_k(layernorm_kernel<OutT, 16>, dim3(grid), dim3(threads), 0, stream, 1, true, x, ldx, group, row_off, row_index, scale, bias, eps,
-                             static_cast<OutT*>(out), ldy, rows, D));
+                             static_cast<OutT*>(out), ldy, rows, D, reverse));
   note_launch();
   return 0;
 }
 
 int layernorm_run(const float* x, int ldx, int group, int row_off, const int* row_index, const float* scale, const float* bias,
-                  float eps, void* out, int out_type, int ldy, int rows, int D, cudaStream_t stream) {
+                  float eps, void* out, int out_type, int ldy, int rows, int D, cudaStream_t stream, int reverse) {
   if (D % 4 != 0 || D > 2048 || ldx % 4 != 0 || ldy % 4 != 0) {
     set_last_error("layernorm: D=%d must be a multiple of 4 and <= 2048 (ldx=%d ldy=%d)", D, ldx, ldy);
     return -1;
   }
   if (rows <= 0) return 0;
-  if (out_type == DT_F32) return ln_launch<float>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
-  if (out_type == DT_TF32) return ln_launch<tf32_t>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
-  if (out_type == DT_F16) return ln_launch<__half>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
-  return ln_launch<__nv_bfloat16>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream);
+  if (out_type == DT_F32) return ln_launch<float>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream, reverse);
+  if (out_type == DT_TF32) return ln_launch<tf32_t>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream, reverse);
+  if (out_type == DT_F16) return ln_launch<__half>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream, reverse);
+  return ln_launch<__nv_bfloat16>(x, ldx, group, row_off, row_index, scale, bias, eps, out, ldy, rows, D, stream, reverse);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -71,6 +71,7 @@ struct EpiDev {
   int act, ldr, out_type, ldo, rows_in, rows_out, row_off, mode;
   int M, N;
   int debug;
+  int reverse;
   int tok_pad, tok_off;  // > 0: 3-D token-scatter reduce-add (see GemmEpilogue)
   int vec;  // 1: N / ldo / ldr multiples of 4 and 16-byte aligned pointers -> vector accesses allowed (generic path)
 };
@@ -367,7 +368,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int te = epi.reverse ? num_tiles - 1 - tile : tile;
+        const int m_blk = te / n_tiles, n_blk = te - m_blk * n_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (PAIR) {
@@ -435,7 +437,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t acc_phase = 0, box_count = 0;
     const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int te = epi.reverse ? num_tiles - 1 - tile : tile;
+      const int m_blk = te / n_tiles, n_blk = te - m_blk * n_tiles;
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BM + q * 32;
       if constexpr (OUT != OUT_GENERIC) {
         // per-tile bias copy (one coalesced 128-bit load per lane of two warps), overlapped with the wait for the MMAs
@@ -643,6 +646,7 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.rows_in = e.rows_in; d.rows_out = e.rows_out; d.row_off = e.row_off; d.mode = e.mode;
   d.M = M; d.N = N;
   d.tok_pad = e.tok_pad; d.tok_off = e.tok_off;
+  d.reverse = e.reverse;
   d.vec = epi_vec_ok(e, N);
   static int dbg = -1;
   if (dbg < 0) { const char* env = getenv("JIMM_GEMM_DEBUG"); dbg = env ? atoi(env) : 0; }
@@ -706,8 +710,11 @@ static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
   }
 }
 
-int gemm_plan_run(const GemmPlan* p, int M_override, cudaStream_t stream) {
-  const int M = (M_override > 0 && M_override <= p->M) ? M_override : p->M;
+int gemm_plan_run(const GemmPlan* p0, int M_override, cudaStream_t stream, int reverse) {
+  const int M = (M_override > 0 && M_override <= p0->M) ? M_override : p0->M;
+  GemmPlan local;
+  const GemmPlan* p = p0;
+  if (reverse != p0->epi.reverse) { local = *p0; local.epi.reverse = reverse; p = &local; }
   switch (p->dtype) {
     case DT_F16: return launch_tc<__half>(p, M, stream);
     case DT_BF16: return launch_tc<__nv_bfloat16>(p, M, stream);

@@ -33,6 +33,7 @@ struct GemmEpilogue {
   // tok_pad rows per sample (multiple of 32); row (b, p) is ADDED to out[b, p + tok_off, :] of a [B, tok_S, N] tensor through a
   // 3-D tensor map (rows p + tok_off >= tok_S are clipped by TMA).  Requires residual == out (pre-initialised with pos-emb).
   int tok_pad = 0, tok_off = 0, tok_S = 0;
+  int reverse = 0;  // walk the M tiles from the end (L2-resident part of the A operand first; see kernels.cuh)
   int rows_in = 0, rows_out = 0, row_off = 0;    // out_row = (r / rows_in) * rows_out + r % rows_in + row_off (rows_in == 0: identity)
   // 2: TMA epilogue (swizzled smem box -> cp.async.bulk.tensor store, cp.reduce .add for the fp32 residual stream; needs
   //    no rowadd / row remap and residual == out) -- falls back to 0 when not applicable;
@@ -52,7 +53,7 @@ struct GemmPlan {
 int gemm_plan_init(GemmPlan* plan, int dtype, const void* A, int lda, const void* B, int ldb, int M, int N, int K,
                    const GemmEpilogue& epi);
 // Enqueue on `stream`; M may be overridden (<= planned M) to run on fewer rows of the same buffers.
-int gemm_plan_run(const GemmPlan* plan, int M_override, cudaStream_t stream);
+int gemm_plan_run(const GemmPlan* plan, int M_override, cudaStream_t stream, int reverse = 0);
 
 // Simple SIMT reference GEMM (debug / bring-up cross-check on the GPU; never on the product path
 // unless JIMM_GEMM_IMPL=simt is set for bisection).

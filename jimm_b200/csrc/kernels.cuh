@@ -1,5 +1,7 @@
 // Host-callable launchers for the non-GEMM kernels of the forward path (elementwise.cu, attention.cu).
 // All enqueue on `stream` and return 0 / negative status (message via jimm_last_error()).
+// `reverse`: walk the rows / tiles / items from the end.  Consecutive kernels of an encoder block alternate direction so each
+// one starts on the data its producer wrote LAST -- the part still resident in the 126 MB L2 (the activations are 77-310 MB).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -12,7 +14,7 @@ namespace jimm {
 //   src row for output r:  r * group + (row_index ? row_index[r] : row_off)      (row stride ldx elements)
 //   out[r, :] (type out_type, row stride ldy) = (x - mean) * rsqrt(max(0, E[x^2]-mean^2) + eps) * scale + bias
 int layernorm_run(const float* x, int ldx, int group, int row_off, const int* row_index, const float* scale, const float* bias,
-                  float eps, void* out, int out_type, int ldy, int rows, int D, cudaStream_t stream);
+                  float eps, void* out, int out_type, int ldy, int rows, int D, cudaStream_t stream, int reverse = 0);
 
 // Patchify: NHWC image (in_type fp32/fp16/bf16) -> A matrix [B*gh*gw, P*P*C] of out_type, row order (b,gy,gx), column
 // order (ky,kx,c) == the HWIO kernel reshape (common/vit.py:153-165,228-230).  128-bit loads.
@@ -45,13 +47,13 @@ int cast_run(const float* src, void* dst, int out_type, size_t n, cudaStream_t s
 
 // Multi-head softmax attention over the fused qkv buffer [B*S, 3D] (q | k | v, heads of 64).  SURVEY 8a row a5.
 //   o[b*S+s, h*64+d] = softmax_k((q/8) k^T  masked) v ; causal: key <= query.  io_type fp16/bf16; out_type fp16/bf16/fp32
-int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
+int attention_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse = 0);
 
 // tcgen05 variant for S <= 256 (attention_tc.cu); returns 1 when the configuration is not handled (caller falls back).
-int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
+int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse = 0);
 
 // tcgen05 two-pass variant for S > 256, non-causal (attention_tc_long.cu); returns 1 when not handled.
-int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream);
+int attention_tc_long_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse = 0);
 
 // MAP-head attention with a single (input-independent) probe query (common/vit.py:96-97).
 //   q: fp32 [H*64] (already projected + biased), kv: [B*S, 2D] (k | v) io_type, out [B, D] out_type

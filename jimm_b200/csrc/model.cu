@@ -187,6 +187,7 @@ struct jimm_model {
   long long prof_launches = 0;
   int epi_mode_16 = 2;  // epilogue mode for 16-bit no-residual outputs (2 = TMA store)
   int epi_mode_res = 2; // epilogue mode for fp32 residual outputs (2 = TMA reduce-add into the residual stream)
+  bool l2_alternate = true;  // JIMM_L2_ALTERNATE=0 disables the alternating walk direction
   bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
 };
 
@@ -325,10 +326,10 @@ struct Packer {
 // ------------------------------------------------------------------------------------------
 // GEMM dispatch (plan-based tcgen05 path; optional SIMT bisection path)
 // ------------------------------------------------------------------------------------------
-static int run_gemm(jimm_model* m, const GemmPlan& p, const void* A, int lda, const LinearW& w, int M, cudaStream_t s) {
+static int run_gemm(jimm_model* m, const GemmPlan& p, const void* A, int lda, const LinearW& w, int M, cudaStream_t s, int reverse = 0) {
   if (M <= 0) return 0;
   if (m->simt) return gemm_simt_run(p.dtype, A, lda, w.w, w.K, M, p.N, p.K, p.epi, s);
-  if (!m->prof_on) return gemm_plan_run(&p, M, s);
+  if (!m->prof_on) return gemm_plan_run(&p, M, s, reverse);
   if (m->prof_used + 2 > m->prof_ev.size()) {
     for (int i = 0; i < 256; ++i) {
       cudaEvent_t e;
@@ -337,7 +338,7 @@ static int run_gemm(jimm_model* m, const GemmPlan& p, const void* A, int lda, co
     }
   }
   JIMM_CUDA_CHECK(cudaEventRecord(m->prof_ev[m->prof_used], s));
-  JIMM_TRY(gemm_plan_run(&p, M, s));
+  JIMM_TRY(gemm_plan_run(&p, M, s, reverse));
   JIMM_CUDA_CHECK(cudaEventRecord(m->prof_ev[m->prof_used + 1], s));
   m->prof_used += 2;
   m->prof_flops += 2.0 * M * static_cast<double>(p.N) * p.K;
@@ -380,14 +381,18 @@ static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s
   const EncoderCfg& c = enc->c;
   Workspace& ws = m->ws;
   const int T = B * S;
+  // Boustrophedon schedule: every kernel walks its rows / tiles / items in the direction opposite to its producer, so it
+  // starts on the data written last -- the part of the 77-310 MB activation still resident in the 126 MB L2.
+  int dir = m->l2_alternate ? 1 : 0;  // the patch GEMM / embedding kernels ran forward -> the first LayerNorm runs backward
+  auto flip = [&]() { const int d = dir; if (m->l2_alternate) dir ^= 1; return d; };
   for (BlockW& b : enc->blocks) {
-    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm1.scale, b.norm1.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s));
-    JIMM_TRY(run_gemm(m, b.p_qkv, ws.h, c.D, b.qkv, T, s));
-    JIMM_TRY(attention_run(ws.big, m->adt, ws.h, m->cdt, B, S, c.H, c.causal, s));
-    JIMM_TRY(run_gemm(m, b.p_out, ws.h, c.D, b.out, T, s));
-    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm2.scale, b.norm2.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s));
-    JIMM_TRY(run_gemm(m, b.p_fc1, ws.h, c.D, b.fc1, T, s));
-    JIMM_TRY(run_gemm(m, b.p_fc2, ws.big, c.M, b.fc2, T, s));
+    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm1.scale, b.norm1.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s, flip()));
+    JIMM_TRY(run_gemm(m, b.p_qkv, ws.h, c.D, b.qkv, T, s, flip()));
+    JIMM_TRY(attention_run(ws.big, m->adt, ws.h, m->cdt, B, S, c.H, c.causal, s, flip()));
+    JIMM_TRY(run_gemm(m, b.p_out, ws.h, c.D, b.out, T, s, flip()));
+    JIMM_TRY(layernorm_run(ws.x, c.D, 1, 0, nullptr, b.norm2.scale, b.norm2.bias, c.eps, ws.h, m->cdt, c.D, T, c.D, s, flip()));
+    JIMM_TRY(run_gemm(m, b.p_fc1, ws.h, c.D, b.fc1, T, s, flip()));
+    JIMM_TRY(run_gemm(m, b.p_fc2, ws.big, c.M, b.fc2, T, s, flip()));
   }
   return 0;
 }
@@ -520,6 +525,7 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   m->adt = cfg->compute_dtype == JIMM_BF16 ? DT_BF16 : DT_F16;
   const char* env = getenv("JIMM_GEMM_IMPL");
   m->simt = env && strcmp(env, "simt") == 0;
+  if ((env = getenv("JIMM_L2_ALTERNATE"))) m->l2_alternate = atoi(env) != 0;
   if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env);
   if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env);
   *out = m;
