@@ -177,8 +177,9 @@ struct jimm_model {
   Workspace ws;
   CommState comm;
   cudaStream_t copy_stream = nullptr;            // host path: H2D of chunk i+1 overlaps the forward of chunk i
-  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
-  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  static constexpr int kHostSlices = 4;
+  cudaEvent_t ev_copied[kHostSlices] = {};
+  cudaEvent_t ev_consumed[kHostSlices] = {};
   cudaEvent_t ev_start = nullptr;
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -733,7 +734,7 @@ int jimm_model_destroy(jimm_model_t* m) {
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   if (m->copy_stream) {
     cudaStreamDestroy(m->copy_stream);
-    for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_consumed[i]); }
+    for (int i = 0; i < jimm_model::kHostSlices; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_consumed[i]); }
     cudaEventDestroy(m->ev_start);
   }
   m->pool.release();
@@ -822,7 +823,7 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (!m->copy_stream) {
     JIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < jimm_model::kHostSlices; ++i) {
       JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
       JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_consumed[i], cudaEventDisableTiming));
     }
@@ -830,22 +831,25 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   }
   const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
   const int od = vision_out_dim(m);
-  // Two-slot pipeline per super-chunk of <= max_batch images: a small first slice (1/4, so little copy time is exposed) and the
-  // rest; the H2D copy of the second slice runs on the side stream while the first slice is in the tower, and the next
-  // super-chunk's first copy overlaps this one's second forward.  The slots partition the staging buffer (max_batch fp32 images).
+  // Sliced pipeline per super-chunk of <= max_batch images: growing slices (1/8, 1/4, rest) so that only the first, small H2D
+  // copy is exposed; slice i+1 is copied on the side stream while slice i is in the tower, and the next super-chunk's first
+  // copy overlaps this one's last forward.  The slices partition the staging buffer (max_batch fp32 images), one event pair each.
   static int head_div = -1;
-  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
+  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 8; }
   const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-  int uses[2] = {0, 0};
+  int uses[jimm_model::kHostSlices] = {};
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
-    int c0 = nb;
-    if (nb >= 128) c0 = ((nb / head_div + 31) / 32) * 32;
-    const int sizes[2] = {c0, nb - c0};
+    int sizes[jimm_model::kHostSlices] = {nb, 0, 0, 0};
+    if (nb >= 128) {
+      const int c0 = ((nb / head_div + 31) / 32) * 32;
+      const int c1 = 2 * c0 < nb - c0 ? 2 * c0 : 0;
+      sizes[0] = c0; sizes[1] = c1; sizes[2] = nb - c0 - c1;
+    }
     int off = 0;
-    for (int slot = 0; slot < 2; ++slot) {
+    for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
       const int n = sizes[slot];
       if (n <= 0) continue;
       uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
@@ -858,10 +862,10 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
       JIMM_TRY(run_vision(m, dst, in_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       ++uses[slot];
-      JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0 + off) * od, out_d, static_cast<size_t>(n) * od * sizeof(float),
-                                      cudaMemcpyDeviceToHost, s));
       off += n;
     }
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s));
   }
   return 0;
 }
