@@ -60,17 +60,6 @@ class NativeModel:
         _lib.check(self.lib.jimm_model_output_dim(self.handle, C.byref(vo), C.byref(to)))
         self.vision_out, self.text_out = vo.value, to.value
         self._comm = None
-        self._pinned_out = {}  # (rows, cols) -> reusable pinned result buffer of the host path
-
-    def _host_out(self, rows: int, cols: int) -> torch.Tensor:
-        key = (rows, cols)
-        t = self._pinned_out.get(key)
-        if t is None:
-            if len(self._pinned_out) > 8:
-                self._pinned_out.clear()
-            t = torch.empty((rows, cols), dtype=torch.float32, pin_memory=True)
-            self._pinned_out[key] = t
-        return t
 
     def close(self):
         if getattr(self, "handle", None):
@@ -115,7 +104,9 @@ class NativeModel:
             return out
         # host path: H2D + forward + D2H enqueued by the library on the current stream
         with torch.cuda.device(self.device):
-            out = self._host_out(B, self.vision_out)
+            # fresh pinned result (torch's caching host allocator makes this cheap); no CPU-side tensor op on this path: an
+            # intra-op OpenMP team on a CPU-quota-limited box costs milliseconds
+            out = torch.empty((B, self.vision_out), dtype=torch.float32, pin_memory=True)
             if encode:
                 xd = x.to(self.device, non_blocking=True)
                 od = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
@@ -126,7 +117,7 @@ class NativeModel:
                 _lib.check(self.lib.jimm_vit_forward_host(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B,
                                                           C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
             torch.cuda.current_stream(self.device).synchronize()
-        return out.clone()  # the pinned buffer is reused by the next call
+        return out
 
     def text(self, ids) -> torch.Tensor:
         ids = self._prep_ids(ids)

@@ -835,7 +835,7 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   // copy is exposed; slice i+1 is copied on the side stream while slice i is in the tower, and the next super-chunk's first
   // copy overlaps this one's last forward.  The slices partition the staging buffer (max_batch fp32 images), one event pair each.
   static int head_div = -1;
-  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 8; }
+  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
   const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
@@ -844,10 +844,39 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
     int sizes[jimm_model::kHostSlices] = {nb, 0, 0, 0};
     if (nb >= 128) {
-      const int c0 = ((nb / head_div + 31) / 32) * 32;
-      const int c1 = 2 * c0 < nb - c0 ? 2 * c0 : 0;
-      sizes[0] = c0; sizes[1] = c1; sizes[2] = nb - c0 - c1;
+      // Two slices: a head slice whose H2D copy is the only exposed one, chosen between nb/8 and nb/3 so that BOTH slices
+      // quantise well into waves of 256-row pair tiles (a badly chosen split costs an extra wave in every GEMM).
+      const int S = m->vis.S, D = m->vis.D, Mm = m->vis.enc.c.M;
+      const int pairs = device_sm_count() / 2;
+      auto cost = [&](int n) {
+        const long mt = (static_cast<long>(n) * S + 255) / 256;
+        auto rounds = [&](int N) { return (mt * ((N + 255) / 256) + pairs - 1) / pairs; };
+        return static_cast<double>(D) * rounds(3 * D) + static_cast<double>(D) * rounds(D) + static_cast<double>(D) * rounds(Mm) +
+               static_cast<double>(Mm) * rounds(D);
+      };
+      int best = nb / head_div;
+      double best_cost = 1e30;
+      for (int c0 = nb / head_div; c0 <= nb / 3; ++c0) {
+        const double cst = cost(c0) + cost(nb - c0) + 1e-3 * c0 * D;  // tie-break towards the smaller exposed copy
+        if (cst < best_cost) { best_cost = cst; best = c0; }
+      }
+      sizes[0] = best;
+      sizes[1] = nb - best;
     }
+    if (const char* env = getenv("JIMM_HOST_SLICES")) {  // experiment hook: explicit comma-separated slice sizes
+      int k = 0, acc = 0;
+      for (const char* q = env; *q && k < jimm_model::kHostSlices - 1;) {
+        const int v = atoi(q);
+        if (v <= 0 || acc + v >= nb) break;
+        sizes[k++] = v;
+        acc += v;
+        while (*q && *q != ',') ++q;
+        if (*q == ',') ++q;
+      }
+      sizes[k] = nb - acc;
+      for (int i = k + 1; i < jimm_model::kHostSlices; ++i) sizes[i] = 0;
+    }
+    static const bool slice_d2h = getenv("JIMM_HOST_SLICE_D2H") && atoi(getenv("JIMM_HOST_SLICE_D2H")) != 0;
     int off = 0;
     for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
       const int n = sizes[slot];
@@ -862,10 +891,14 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
       JIMM_TRY(run_vision(m, dst, in_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       ++uses[slot];
+      if (slice_d2h)
+        JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0 + off) * od, out_d, static_cast<size_t>(n) * od * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s));
       off += n;
     }
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
-                                    cudaMemcpyDeviceToHost, s));
+    if (!slice_d2h)
+      JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
+                                      cudaMemcpyDeviceToHost, s));
   }
   return 0;
 }
