@@ -815,68 +815,78 @@ int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, co
 }
 
 // ---- forward, host buffers ----
+static int ensure_copy_stream(jimm_model* m) {
+  if (m->copy_stream) return 0;
+  JIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < jimm_model::kHostSlices; ++i) {
+    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_consumed[i], cudaEventDisableTiming));
+  }
+  JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+  return 0;
+}
+
+// Slice schedule of one super-chunk of nb images on the host path.  Two slices: a head slice whose H2D copy is the only exposed
+// one, chosen between nb/head_div and nb/3 so that BOTH slices quantise well into waves of 256-row pair tiles (a badly chosen
+// split costs an extra wave in every GEMM: 64 images take 3.3 ms on ViT-B/16 where 62 take 2.8 ms).  JIMM_HOST_SLICES (comma
+// separated sizes) overrides it for experiments.
+static void host_slices(const jimm_model* m, int nb, int* sizes) {
+  for (int i = 0; i < jimm_model::kHostSlices; ++i) sizes[i] = 0;
+  sizes[0] = nb;
+  if (const char* env = getenv("JIMM_HOST_SLICES")) {
+    int k = 0, acc = 0;
+    for (const char* q = env; *q && k < jimm_model::kHostSlices - 1;) {
+      const int v = atoi(q);
+      if (v <= 0 || acc + v >= nb) break;
+      sizes[k++] = v;
+      acc += v;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    sizes[k] = nb - acc;
+    return;
+  }
+  if (nb < 128) return;
+  static int head_div = -1;
+  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
+  const int S = m->vis.S, D = m->vis.D, Mm = m->vis.enc.c.M;
+  const int pairs = device_sm_count() / 2;
+  auto cost = [&](int n) {
+    const long mt = (static_cast<long>(n) * S + 255) / 256;
+    auto rounds = [&](int N) { return (mt * ((N + 255) / 256) + pairs - 1) / pairs; };
+    return static_cast<double>(D) * rounds(3 * D) + static_cast<double>(D) * rounds(D) + static_cast<double>(D) * rounds(Mm) +
+           static_cast<double>(Mm) * rounds(D);
+  };
+  int best = nb / head_div;
+  double best_cost = 1e30;
+  for (int c0 = nb / head_div; c0 <= nb / 3; ++c0) {
+    const double cst = cost(c0) + cost(nb - c0) + 1e-3 * c0 * D;  // tie-break towards the smaller exposed copy
+    if (cst < best_cost) { best_cost = cst; best = c0; }
+  }
+  sizes[0] = best;
+  sizes[1] = nb - best;
+}
+
 int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream) {
   JIMM_TRY(check_ready(m, B));
   if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
   if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host on a dual-tower model"); return JIMM_EINVAL; }
   JIMM_TRY(set_device(m));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (!m->copy_stream) {
-    JIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < jimm_model::kHostSlices; ++i) {
-      JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
-      JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_consumed[i], cudaEventDisableTiming));
-    }
-    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
-  }
-  const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
-  const int od = vision_out_dim(m);
-  // Sliced pipeline per super-chunk of <= max_batch images: growing slices (1/8, 1/4, rest) so that only the first, small H2D
-  // copy is exposed; slice i+1 is copied on the side stream while slice i is in the tower, and the next super-chunk's first
-  // copy overlaps this one's last forward.  The slices partition the staging buffer (max_batch fp32 images), one event pair each.
-  static int head_div = -1;
-  if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
+  JIMM_TRY(ensure_copy_stream(m));
   const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
+  const size_t img_bytes = img_elems * dtype_size(in_dtype);
+  const int od = vision_out_dim(m);
+  // Sliced pipeline per super-chunk of <= max_batch images: slice i+1 is copied on the side stream while slice i is in the
+  // tower, and the next super-chunk's first copy overlaps this one's last forward.  The slices partition the staging buffer
+  // (max_batch fp32 images), one event pair each; one D2H of the super-chunk's result at its end.
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
   int uses[jimm_model::kHostSlices] = {};
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
-    int sizes[jimm_model::kHostSlices] = {nb, 0, 0, 0};
-    if (nb >= 128) {
-      // Two slices: a head slice whose H2D copy is the only exposed one, chosen between nb/8 and nb/3 so that BOTH slices
-      // quantise well into waves of 256-row pair tiles (a badly chosen split costs an extra wave in every GEMM).
-      const int S = m->vis.S, D = m->vis.D, Mm = m->vis.enc.c.M;
-      const int pairs = device_sm_count() / 2;
-      auto cost = [&](int n) {
-        const long mt = (static_cast<long>(n) * S + 255) / 256;
-        auto rounds = [&](int N) { return (mt * ((N + 255) / 256) + pairs - 1) / pairs; };
-        return static_cast<double>(D) * rounds(3 * D) + static_cast<double>(D) * rounds(D) + static_cast<double>(D) * rounds(Mm) +
-               static_cast<double>(Mm) * rounds(D);
-      };
-      int best = nb / head_div;
-      double best_cost = 1e30;
-      for (int c0 = nb / head_div; c0 <= nb / 3; ++c0) {
-        const double cst = cost(c0) + cost(nb - c0) + 1e-3 * c0 * D;  // tie-break towards the smaller exposed copy
-        if (cst < best_cost) { best_cost = cst; best = c0; }
-      }
-      sizes[0] = best;
-      sizes[1] = nb - best;
-    }
-    if (const char* env = getenv("JIMM_HOST_SLICES")) {  // experiment hook: explicit comma-separated slice sizes
-      int k = 0, acc = 0;
-      for (const char* q = env; *q && k < jimm_model::kHostSlices - 1;) {
-        const int v = atoi(q);
-        if (v <= 0 || acc + v >= nb) break;
-        sizes[k++] = v;
-        acc += v;
-        while (*q && *q != ',') ++q;
-        if (*q == ',') ++q;
-      }
-      sizes[k] = nb - acc;
-      for (int i = k + 1; i < jimm_model::kHostSlices; ++i) sizes[i] = 0;
-    }
-    static const bool slice_d2h = getenv("JIMM_HOST_SLICE_D2H") && atoi(getenv("JIMM_HOST_SLICE_D2H")) != 0;
+    int sizes[jimm_model::kHostSlices];
+    host_slices(m, nb, sizes);
     int off = 0;
     for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
       const int n = sizes[slot];
@@ -891,14 +901,10 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
       JIMM_TRY(run_vision(m, dst, in_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       ++uses[slot];
-      if (slice_d2h)
-        JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0 + off) * od, out_d, static_cast<size_t>(n) * od * sizeof(float),
-                                        cudaMemcpyDeviceToHost, s));
       off += n;
     }
-    if (!slice_d2h)
-      JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
-                                      cudaMemcpyDeviceToHost, s));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
+                                    cudaMemcpyDeviceToHost, s));
   }
   return 0;
 }
@@ -909,12 +915,41 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
   if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
   if (Bi > m->max_batch || Bt > m->max_batch) { set_last_error("dual_forward_host: batch (%d,%d) exceeds max_batch %d", Bi, Bt, m->max_batch); return JIMM_EINVAL; }
   if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  if (T <= 0 || T > m->txt.T) { set_last_error("sequence length %d outside (0, context_length=%d]", T, m->txt.T); return JIMM_EINVAL; }
   JIMM_TRY(set_device(m));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t img_bytes = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C * dtype_size(in_dtype);
-  JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, img_host, Bi * img_bytes, cudaMemcpyHostToDevice, s));
+  JIMM_TRY(ensure_copy_stream(m));
+  const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
+  const size_t img_bytes = img_elems * dtype_size(in_dtype);
+  const int E = m->txt.D;
+  // The (large) image copy goes to the side stream in slices while the caller's stream takes the token ids and runs the
+  // text tower; the vision tower then consumes each image slice as its copy lands.
+  JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
+  JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+  int sizes[jimm_model::kHostSlices];
+  host_slices(m, Bi, sizes);
+  int off = 0;
+  for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
+    const int n = sizes[slot];
+    if (n <= 0) continue;
+    uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + static_cast<size_t>(off) * img_bytes, n * img_bytes,
+                                    cudaMemcpyHostToDevice, m->copy_stream));
+    JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
+    off += n;
+  }
   JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids_host, static_cast<size_t>(Bt) * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-  JIMM_TRY(jimm_dual_forward(m, m->ws.in_img, in_dtype, Bi, m->ws.in_ids, Bt, T, m->ws.out_dev, stream));
+  JIMM_TRY(run_text(m, m->ws.in_ids, Bt, T, m->ws.emb_t, s));
+  off = 0;
+  for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
+    const int n = sizes[slot];
+    if (n <= 0) continue;
+    const uint8_t* src = static_cast<const uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
+    JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
+    JIMM_TRY(run_vision(m, src, in_dtype, n, m->ws.emb_i + static_cast<size_t>(off) * E, s));
+    off += n;
+  }
+  JIMM_TRY(jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, m->ws.out_dev, stream));
   JIMM_CUDA_CHECK(cudaMemcpyAsync(logits_host, m->ws.out_dev, static_cast<size_t>(Bi) * Bt * sizeof(float), cudaMemcpyDeviceToHost, s));
   return 0;
 }

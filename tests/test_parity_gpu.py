@@ -282,6 +282,11 @@ def test_dual_tower_medium(kind):
     # host path
     out_h = m(img, txt.to(torch.int32))
     assert torch.equal(out_h, out.cpu())
+    # host path at a batch large enough for the sliced H2D pipeline (image slices on the side stream, text tower meanwhile)
+    big = O.synthetic_images(160, 64, seed=5)
+    m.set_max_batch(160)
+    out_b = m(big.cuda(), txt.cuda())
+    assert torch.equal(m(big.pin_memory(), txt.to(torch.int32).pin_memory()), out_b.cpu())
     # shorter sequences use positional_embedding[:seq] and the sliced mask (common/transformer.py:125-129)
     if kind == "clip":
         with torch.no_grad():
