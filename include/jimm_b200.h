@@ -129,6 +129,29 @@ JIMM_API int jimm_k_embed(const int32_t* ids, const float* table, const float* p
 JIMM_API int jimm_k_l2_normalize(const float* x, float* out, int ldo, int B, int E, void* stream);
 JIMM_API int jimm_k_logits(const float* img, const float* txt, const float* logit_scale, const float* logit_bias, float* logits, int Bi, int Bt,
                   int E, int ldl, void* stream);
+/* ---- image front-end: the HuggingFace image processor the reference's examples run on the host ----
+ * Replaces `processor(images=..., return_tensors="np")["pixel_values"]` + the NCHW->NHWC transpose of
+ * examples/vit_inference.py:27-37, examples/clip_inference.py:35-38 (transformers 4.53.0 slow processors on Pillow 11.3.0,
+ * uv.lock:2679,1573): Pillow 8-bit resize with antialiasing (bilinear | bicubic) -> optional centre crop -> rescale ->
+ * normalise, written NHWC in the dtype the tower consumes.  Bit-exact with that pipeline (integer resampling, IEEE fp32
+ * rescale/normalise).  Mirrors `preprocessor_config.json`: size {height,width} | {shortest_edge}, crop_size, resample,
+ * rescale_factor, image_mean, image_std. */
+typedef struct jimm_preproc jimm_preproc_t;
+typedef struct jimm_preproc_config {
+  int height, width;        /* exact output size (ViT, SigLIP: size = {height, width}) ... */
+  int shortest_edge;        /* ... or, when non-zero, resize the shortest edge to this keeping the aspect ratio (CLIP) */
+  int crop_h, crop_w;       /* centre crop after the resize (CLIP crop_size); 0 = none */
+  int resample;             /* PIL code: 2 bilinear, 3 bicubic */
+  double rescale_factor;    /* 1/255 */
+  float mean[3], std[3];    /* image_mean, image_std */
+} jimm_preproc_config_t;
+JIMM_API int jimm_preproc_create(const jimm_preproc_config_t* cfg, int device, jimm_preproc_t** out);
+JIMM_API int jimm_preproc_output_size(const jimm_preproc_t* p, int H, int W, int* out_h, int* out_w);
+/* img: device uint8 [B,H,W,3] (same-sized RGB images); out: device [B,out_h,out_w,3] of out_dtype (JIMM_F32 | JIMM_F16 | JIMM_BF16). */
+JIMM_API int jimm_preproc_run(jimm_preproc_t* p, const uint8_t* img, int B, int H, int W, void* out, int out_dtype, void* stream);
+JIMM_API int jimm_preproc_destroy(jimm_preproc_t* p);
+/* Host-only test entry: Pillow's resampling windows and 22-bit fixed-point weights for one axis. */
+JIMM_API int jimm_k_resample_coeffs(int in_size, int out_size, int resample, int* ksize, int* first, int* count, int* kk, int kk_capacity);
 /* Live timing of the dominant kernel (the tcgen05 GEMM) inside a forward: between begin and end every GEMM launch is
  * bracketed by CUDA events on the launch stream; end synchronises and returns the summed device time (ms), the
  * algorithmic FLOPs (2*M*N*K per launch) and the number of launches.  Used by bench.py's roofline object. */

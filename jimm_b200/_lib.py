@@ -38,6 +38,15 @@ class Config(C.Structure):
 _vp, _i, _f, _fp, _ip = C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p
 
 # name -> (restype, argtypes): every symbol include/jimm_b200.h declares
+class PreprocConfig(C.Structure):
+    """jimm_preproc_config_t"""
+
+    _fields_ = [
+        ("height", C.c_int), ("width", C.c_int), ("shortest_edge", C.c_int), ("crop_h", C.c_int), ("crop_w", C.c_int),
+        ("resample", C.c_int), ("rescale_factor", C.c_double), ("mean", C.c_float * 3), ("std", C.c_float * 3),
+    ]
+
+
 SIGNATURES = {
     "jimm_last_error": (C.c_char_p, []),
     "jimm_abi_version": (_i, []),
@@ -69,6 +78,11 @@ SIGNATURES = {
     "jimm_k_embed": (_i, [_ip, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "jimm_k_l2_normalize": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "jimm_k_logits": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
+    "jimm_preproc_create": (_i, [C.POINTER(PreprocConfig), _i, C.POINTER(_vp)]),
+    "jimm_preproc_output_size": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "jimm_preproc_run": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp]),
+    "jimm_preproc_destroy": (_i, [_vp]),
+    "jimm_k_resample_coeffs": (_i, [_i, _i, _i, C.POINTER(_i), _ip, _ip, _ip, _i]),
 }
 
 _lib = None
