@@ -159,6 +159,9 @@ JIMM_API int jimm_profile_begin(jimm_model_t* m);
 JIMM_API int jimm_profile_end(jimm_model_t* m, double* gemm_ms, double* gemm_flops, long long* gemm_launches);
 /* Count of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 JIMM_API long long jimm_launch_count(void);
+/* Count of tower forwards replayed from a captured CUDA graph (batches <= JIMM_GRAPH_MAX_BATCH, default 32, from the
+ * second call of a shape on); their kernels are included in jimm_launch_count. */
+JIMM_API long long jimm_graph_replay_count(void);
 
 #ifdef __cplusplus
 }

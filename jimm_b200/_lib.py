@@ -51,6 +51,7 @@ SIGNATURES = {
     "jimm_last_error": (C.c_char_p, []),
     "jimm_abi_version": (_i, []),
     "jimm_launch_count": (C.c_longlong, []),
+    "jimm_graph_replay_count": (C.c_longlong, []),
     "jimm_model_create": (_i, [C.POINTER(Config), _i, C.POINTER(_vp)]),
     "jimm_model_set_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _i, _i]),
     "jimm_model_finalize": (_i, [_vp, _i]),

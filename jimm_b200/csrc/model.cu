@@ -14,6 +14,7 @@
 #include <atomic>
 #include <cmath>
 #include <map>
+#include <tuple>
 #include <memory>
 #include <string>
 #include <vector>
@@ -37,6 +38,7 @@ void set_last_error(const char* fmt, ...) {
   va_end(ap);
 }
 static std::atomic<long long> g_launches{0};
+static std::atomic<long long> g_graph_replays{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int pdl_enabled() {
   static int v = -1;
@@ -190,6 +192,17 @@ struct jimm_model {
   int epi_mode_res = 2; // epilogue mode for fp32 residual outputs (2 = TMA reduce-add into the residual stream)
   bool l2_alternate = true;  // JIMM_L2_ALTERNATE=0 disables the alternating walk direction
   bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
+  // CUDA-graph replay of a whole tower for small batches (launch-bound regime; config 1 is B=4): the second call of a
+  // (tower, batch, dtype | length) shape is stream-captured from fixed staging buffers, later calls replay it.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    int seen = 0;
+  };
+  std::map<std::tuple<int, int, int>, GraphEntry> graphs;
+  int graph_max_batch = 32;  // JIMM_GRAPH_MAX_BATCH (0 disables)
+  float* graph_out = nullptr;  // [graph_max_batch, max(vision out, E)]
+  cudaStream_t capture_stream = nullptr;
 };
 
 namespace jimm {
@@ -474,6 +487,87 @@ static int set_device(const jimm_model* m) {
 
 static int vision_out_dim(const jimm_model* m) { return m->vis.head.N > 0 ? m->vis.head.N : m->vis.D; }
 
+// ------------------------------------------------------------------------------------------
+// CUDA-graph replay for small batches
+// ------------------------------------------------------------------------------------------
+static void graphs_release(jimm_model* m) {
+  for (auto& kv : m->graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  m->graphs.clear();
+}
+
+// Runs `body` (which enqueues a tower on `s`, reading and writing fixed workspace buffers only) eagerly the first time a key is
+// seen, captures it into a graph the second time, and replays the graph afterwards.  Any capture problem disables graphs for
+// the model and falls back to the eager launches -- the same kernels either way.
+template <typename F>
+static int run_graphed(jimm_model* m, std::tuple<int, int, int> key, cudaStream_t s, F&& body) {
+  if (m->graph_max_batch <= 0 || m->prof_on || m->simt) return body(s);
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {  // the caller is capturing already
+    cudaGetLastError();
+    return body(s);
+  }
+  jimm_model::GraphEntry& e = m->graphs[key];
+  if (e.exec) {
+    JIMM_CUDA_CHECK(cudaGraphLaunch(e.exec, s));
+    g_launches.fetch_add(e.launches, std::memory_order_relaxed);
+    g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  if (e.seen++ == 0) return body(s);
+  // Capture on a private stream: the caller's stream may be the legacy default stream, which cannot be captured; nothing
+  // executes during capture, and the instantiated graph is launched on the caller's stream.
+  if (!m->capture_stream && cudaStreamCreateWithFlags(&m->capture_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    m->graph_max_batch = 0;
+    return body(s);
+  }
+  const long long l0 = g_launches.load();
+  if (cudaStreamBeginCapture(m->capture_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    m->graph_max_batch = 0;
+    return body(s);
+  }
+  const int rc = body(m->capture_stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(m->capture_stream, &g);
+  const long long captured = g_launches.load() - l0;
+  g_launches.fetch_sub(captured, std::memory_order_relaxed);  // captured launches have not run
+  cudaGraphExec_t exec = nullptr;
+  if (rc == 0 && ce == cudaSuccess && g && cudaGraphInstantiate(&exec, g, 0) == cudaSuccess) {
+    cudaGraphDestroy(g);
+    e.exec = exec;
+    e.launches = captured;
+    JIMM_CUDA_CHECK(cudaGraphLaunch(e.exec, s));
+    g_launches.fetch_add(e.launches, std::memory_order_relaxed);
+    g_graph_replays.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+  if (g) cudaGraphDestroy(g);
+  cudaGetLastError();
+  m->graph_max_batch = 0;
+  if (rc != 0) return rc;
+  return body(s);
+}
+
+// Vision tower of one chunk.  Small chunks go through the graph: input staged into ws.in_img, result from m->graph_out.
+static int exec_vision(jimm_model* m, const void* img, int in_dtype, int n, float* out, cudaStream_t s) {
+  if (n <= 0 || n > m->graph_max_batch || !m->graph_out) return run_vision(m, img, in_dtype, n, out, s);
+  const size_t bytes = static_cast<size_t>(n) * m->vis.img * m->vis.img * m->vis.C * dtype_size(in_dtype);
+  if (img != m->ws.in_img) JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, img, bytes, cudaMemcpyDeviceToDevice, s));
+  JIMM_TRY(run_graphed(m, std::make_tuple(0, n, in_dtype), s, [&](cudaStream_t cs) { return run_vision(m, m->ws.in_img, in_dtype, n, m->graph_out, cs); }));
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(out, m->graph_out, static_cast<size_t>(n) * vision_out_dim(m) * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+static int exec_text(jimm_model* m, const int32_t* ids, int n, int T, float* out, cudaStream_t s) {
+  if (n <= 0 || n > m->graph_max_batch || !m->graph_out) return run_text(m, ids, n, T, out, s);
+  if (ids != m->ws.in_ids) JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids, static_cast<size_t>(n) * T * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  JIMM_TRY(run_graphed(m, std::make_tuple(1, n, T), s, [&](cudaStream_t cs) { return run_text(m, m->ws.in_ids, n, T, m->graph_out, cs); }));
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(out, m->graph_out, static_cast<size_t>(n) * m->txt.D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
 }  // namespace jimm
 
 // ==========================================================================================
@@ -484,6 +578,7 @@ extern "C" {
 const char* jimm_last_error(void) { return g_err; }
 int jimm_abi_version(void) { return 1; }
 long long jimm_launch_count(void) { return g_launches.load(); }
+long long jimm_graph_replay_count(void) { return g_graph_replays.load(); }
 
 int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) {
   if (!cfg || !out) { set_last_error("jimm_model_create: null argument"); return JIMM_EINVAL; }
@@ -527,6 +622,7 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   const char* env = getenv("JIMM_GEMM_IMPL");
   m->simt = env && strcmp(env, "simt") == 0;
   if ((env = getenv("JIMM_L2_ALTERNATE"))) m->l2_alternate = atoi(env) != 0;
+  if ((env = getenv("JIMM_GRAPH_MAX_BATCH"))) m->graph_max_batch = atoi(env) > 0 ? atoi(env) : 0;
   if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env);
   if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env);
   *out = m;
@@ -686,6 +782,12 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   ws.out_dev_elems = dual ? Bm * Bm : Bm * vision_out_dim(m);
   if (ws.out_dev_elems < Bm * E) ws.out_dev_elems = Bm * E;
   if ((rc = m->pool.alloc(&p, ws.out_dev_elems * sizeof(float)))) return rc; ws.out_dev = static_cast<float*>(p);
+  if (m->graph_max_batch > 0) {
+    const size_t gw = static_cast<size_t>(vision_out_dim(m)) > E ? vision_out_dim(m) : E;
+    const size_t gb = static_cast<size_t>(m->graph_max_batch) < Bm ? m->graph_max_batch : Bm;
+    if ((rc = m->pool.alloc(&p, gb * gw * sizeof(float)))) return rc;
+    m->graph_out = static_cast<float*>(p);
+  }
 
   // ---- GEMM plans (TMA descriptors bound to the fixed workspace / weight buffers) ----
   if (v.patch_scatter) {
@@ -731,6 +833,8 @@ int jimm_model_destroy(jimm_model_t* m) {
   cudaSetDevice(m->device);
   cudaDeviceSynchronize();
   comm_destroy(&m->comm);
+  graphs_release(m);
+  if (m->capture_stream) cudaStreamDestroy(m->capture_stream);
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   if (m->copy_stream) {
     cudaStreamDestroy(m->copy_stream);
@@ -758,14 +862,14 @@ static int vision_chunks(jimm_model* m, const void* img, int in_dtype, int B, fl
   const int od = vision_out_dim(m);
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
-    JIMM_TRY(run_vision(m, static_cast<const uint8_t*>(img) + b0 * img_elems * in_es, in_dtype, nb, out + static_cast<size_t>(b0) * od, s));
+    JIMM_TRY(exec_vision(m, static_cast<const uint8_t*>(img) + b0 * img_elems * in_es, in_dtype, nb, out + static_cast<size_t>(b0) * od, s));
   }
   return 0;
 }
 static int text_chunks(jimm_model* m, const int32_t* ids, int B, int T, float* out, cudaStream_t s) {
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
-    JIMM_TRY(run_text(m, ids + static_cast<size_t>(b0) * T, nb, T, out + static_cast<size_t>(b0) * m->txt.D, s));
+    JIMM_TRY(exec_text(m, ids + static_cast<size_t>(b0) * T, nb, T, out + static_cast<size_t>(b0) * m->txt.D, s));
   }
   return 0;
 }
@@ -898,7 +1002,7 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
                                       cudaMemcpyHostToDevice, m->copy_stream));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
       JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
-      JIMM_TRY(run_vision(m, dst, in_dtype, n, out_d, s));
+      JIMM_TRY(exec_vision(m, dst, in_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       ++uses[slot];
       off += n;
@@ -943,14 +1047,14 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
     JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
     off += n;
   }
-  JIMM_TRY(run_text(m, m->ws.in_ids, Bt, T, m->ws.emb_t, s));
+  JIMM_TRY(exec_text(m, m->ws.in_ids, Bt, T, m->ws.emb_t, s));
   off = 0;
   for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
     const int n = sizes[slot];
     if (n <= 0) continue;
     const uint8_t* src = static_cast<const uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
     JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
-    JIMM_TRY(run_vision(m, src, in_dtype, n, m->ws.emb_i + static_cast<size_t>(off) * E, s));
+    JIMM_TRY(exec_vision(m, src, in_dtype, n, m->ws.emb_i + static_cast<size_t>(off) * E, s));
     off += n;
   }
   JIMM_TRY(jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, m->ws.out_dev, stream));

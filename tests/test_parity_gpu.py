@@ -332,3 +332,56 @@ def test_simt_bisection_path_agrees(vitb16, monkeypatch):
     b = _set(VisionTransformer(num_classes=12, img_size=32, patch_size=8, num_layers=2, num_heads=2, mlp_dim=256, hidden_size=128,
                                dtype=torch.float16), ps)(x)
     assert rel(a, b) < 1e-3
+
+
+def test_small_batch_graph_replay(vitb16):
+    """Small batches replay a captured CUDA graph from the third call on: same bits as the eager launches, fresh inputs honoured,
+    launch accounting unchanged (config 1 is B=4)."""
+    from jimm_b200 import _lib
+    from jimm_b200.models import VisionTransformer
+
+    cfg, p, img, ref = vitb16
+    lib = _lib.load()
+    m = _set(VisionTransformer(dtype=torch.float16), p).eval()
+    x = img.cuda()
+    m(x[:1])  # builds the native handle (one-off packing kernels)
+    torch.cuda.synchronize()
+    l0, g0 = lib.jimm_launch_count(), lib.jimm_graph_replay_count()
+    eager = m(x)  # first call of the shape: eager
+    torch.cuda.synchronize()
+    per_call = lib.jimm_launch_count() - l0
+    assert lib.jimm_graph_replay_count() == g0
+    outs = [m(x) for _ in range(3)]  # capture, then replays
+    torch.cuda.synchronize()
+    assert lib.jimm_graph_replay_count() - g0 == 3
+    assert lib.jimm_launch_count() - l0 == 4 * per_call
+    for o in outs:
+        assert torch.equal(o, eager)
+    assert rel(eager, ref) < TOL
+    # a different input through the replayed graph, on a side stream
+    y = torch.flip(x, dims=[0]).contiguous()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        flipped = m(y)
+    s.synchronize()
+    assert torch.equal(flipped, torch.flip(eager, dims=[0]))
+    # host path of the same small batch
+    assert torch.equal(m(img), eager.cpu())
+
+
+def test_small_batch_graph_replay_dual():
+    """Both towers of a dual model replay their graphs (text keyed by batch and sequence length)."""
+    from jimm_b200.models import CLIP
+
+    m = CLIP(64, 2, 128, 16, 20, 300, 64, 1, 2, dtype=torch.float16)
+    img = O.synthetic_images(5, 64, seed=3).cuda()
+    txt = O.synthetic_tokens(7, 20, 300, "clip", seed=4).to(torch.int32).cuda()
+    first = m(img, txt)
+    for _ in range(3):
+        assert torch.equal(m(img, txt), first)
+    assert torch.equal(m(torch.flip(img, dims=[0]).contiguous(), txt), torch.flip(first, dims=[0]))
+    full = m.encode_text(txt)
+    for _ in range(3):
+        assert torch.equal(m.encode_text(txt[:3].contiguous()), full[:3])
+        assert torch.equal(m.encode_text(txt[:, :11].contiguous()), m.encode_text(txt[:, :11].contiguous()))
