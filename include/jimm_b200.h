@@ -152,6 +152,13 @@ JIMM_API int jimm_preproc_run(jimm_preproc_t* p, const uint8_t* img, int B, int 
 JIMM_API int jimm_preproc_destroy(jimm_preproc_t* p);
 /* Host-only test entry: Pillow's resampling windows and 22-bit fixed-point weights for one axis. */
 JIMM_API int jimm_k_resample_coeffs(int in_size, int out_size, int resample, int* ksize, int* first, int* count, int* kk, int kk_capacity);
+/* ---- zero-shot / classification epilogue: what the examples compute in JAX after the forward ----
+ * logits: device fp32 [rows, cols] (leading dimension ld).  mode 0: probs = exp(x) / sum(exp(x)) per row, un-shifted like
+ * examples/clip_inference.py:47; mode 1: probs = sigmoid(x) (SigLIP pair probabilities).  order (nullable, int32 [rows, cols]):
+ * `argsort(x)[::-1]` per row -- descending, equal scores with the larger index first (examples/clip_inference.py:49);
+ * argmax (nullable, int32 [rows]): first maximum per row (examples/vit_inference.py:58).  order / argmax need cols <= 4096. */
+JIMM_API int jimm_postprocess(const float* logits, int rows, int cols, int ld, int mode, float* probs, int ldp, int32_t* order, int32_t* argmax,
+                              void* stream);
 /* Live timing of the dominant kernel (the tcgen05 GEMM) inside a forward: between begin and end every GEMM launch is
  * bracketed by CUDA events on the launch stream; end synchronises and returns the summed device time (ms), the
  * algorithmic FLOPs (2*M*N*K per launch) and the number of launches.  Used by bench.py's roofline object. */

@@ -182,3 +182,20 @@ def synthetic_u8_images(B: int, h: int, w: int, seed: int = 1234) -> np.ndarray:
     up = np.repeat(np.repeat(base, 8, axis=1), 8, axis=2)[:, :h, :w]
     noise = rng.integers(-96, 97, size=(B, h, w, 3)).astype(np.float32)
     return np.clip(up + noise, 0, 255).astype(np.uint8)
+
+
+# ---- zero-shot / classification epilogue ----
+def zero_shot_oracle(logits: np.ndarray):
+    """examples/clip_inference.py:46-51 per row: un-shifted softmax in float32 and `argsort(scores)[::-1]` (stable ascending
+    sort reversed: equal scores come out with the larger index first)."""
+    x = np.asarray(logits, dtype=np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        e = np.exp(x)  # float32 like jnp.exp on the float32 logits: overflows to inf above ~88.7, the row then holds NaN / 0
+        probs = (e.astype(np.float64) / e.astype(np.float64).sum(axis=-1, keepdims=True)).astype(np.float32)
+    order = np.argsort(x, axis=-1, kind="stable")[..., ::-1].astype(np.int32)
+    return probs, order
+
+
+def classify_oracle(logits: np.ndarray) -> np.ndarray:
+    """examples/vit_inference.py:58: first maximum per row."""
+    return np.argmax(np.asarray(logits, dtype=np.float32), axis=-1).astype(np.int32)
