@@ -61,6 +61,12 @@ class NativeModel:
         self.vision_out, self.text_out = vo.value, to.value
         self._comm = None
 
+    def side_stream(self) -> torch.cuda.Stream:
+        """Copy stream for host inputs of the multi-GPU dual path."""
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.jimm_model_destroy(self.handle)

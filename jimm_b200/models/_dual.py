@@ -89,9 +89,36 @@ class DualTower(_NativeOwner, nn.Module):
 
         B = image.shape[0]
         n = self.native(B, require=True)
-        ie = self.encode_image(image if image.is_cuda else image.to(n.device, non_blocking=True)) if isinstance(image, torch.Tensor) \
-            else self.encode_image(torch.as_tensor(image).to(n.device))
-        te = n.text(text if isinstance(text, torch.Tensor) else torch.as_tensor(text)).to(n.device)
+        x, ids = n._prep_images(image), n._prep_ids(text)
+        host_in = not x.is_cuda and not ids.is_cuda
+        with torch.cuda.device(n.device):
+            cur = torch.cuda.current_stream(n.device)
+            # host inputs: the ids go first (H2D copies share one engine), the images follow on a side stream and land while
+            # the text tower runs -- the same overlap as the single-GPU host path (csrc/model.cu jimm_dual_forward_host)
+            ids_d = ids if ids.is_cuda else ids.to(n.device, non_blocking=True)
+            if x.is_cuda:
+                x_d = x
+            else:
+                side = n.side_stream()
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    x_d = x.to(n.device, non_blocking=True)
+            te = n.text(ids_d)
+            if not x.is_cuda:
+                cur.wait_stream(side)
+                x_d.record_stream(cur)
+            ie = n.vision(x_d, encode=True)
+            out = self._distributed_logits(n, ie, te, B)
+            if not host_in:
+                return out
+            out_h = torch.empty(out.shape, dtype=torch.float32, pin_memory=True)
+            out_h.copy_(out, non_blocking=True)
+            cur.synchronize()
+            return out_h
+
+    def _distributed_logits(self, n, ie, te, B) -> torch.Tensor:
+        import torch.distributed as dist
+
         if (self._comm_mode or "peer") == "peer":
             if n._comm is None or n._comm[2] < B:
                 n.comm_setup(max(B, n.max_batch))

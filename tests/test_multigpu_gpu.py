@@ -59,6 +59,10 @@ def _worker(rank, world, port, kind, q):
         else:
             assert float((out.cpu() - full[lo:hi]).abs().max()) < 1e-4
         errs.append(float((out.cpu().double() - ref[lo:hi].double()).abs().max() / ref.abs().max()))
+    # host inputs: ids first, images on a side stream under the text tower, pinned host result
+    m.set_comm("peer")
+    out_h = m(img[lo:hi].pin_memory(), txt[lo:hi].to(torch.int32).pin_memory())
+    assert not out_h.is_cuda and torch.equal(out_h, full[lo:hi])
     torch.cuda.synchronize()
     dist.barrier()
     q.put((rank, errs))
