@@ -1,14 +1,16 @@
 // tcgen05 softmax attention for sequences longer than 256 tokens (non-causal), head_dim 64:
 // ViT-L/16@384 (S = 576) and SigLIP2-L/16@512 (S = 1024) -- BASELINE configs 3 and 5.
 //
-// Two passes over the keys instead of online-softmax rescaling (the O accumulator lives in TMEM; rescaling it would cost a
-// TMEM round trip per key block): pass A recomputes S = Q K^T block by block only to find each row's maximum, pass B
-// recomputes S, writes P = exp2((S - max) * scale) over it in place (16-bit, tensor memory) and accumulates O += P V with
-// the tensor core's own accumulate flag.  The extra Q K^T costs 0.5x tensor work; the kernel is MUFU(exp2)-bound anyway.
+// One pass over the keys with a lazily raised reference maximum: P = exp2((S - m_ref) * scale) is written over S in place
+// (16-bit, tensor memory) and O += P V accumulates with the tensor core's own accumulate flag.  m_ref starts at the maximum of
+// the row's first 32 scores and is only replaced when a later 32-score chunk exceeds it by more than 8 in the log2 domain
+// (P <= 2^8 stays comfortably inside fp16), which almost never happens; when it does, the row's running sum, the P chunks already
+// written for the current block and the O accumulator (a 64-column TMEM round trip, after the previous P V has completed) are
+// multiplied by 2^(old - new).  O / l at the end is the exact softmax whatever the reference was.  (The earlier two-pass version
+// recomputed Q K^T for the row maxima first: 1.5x the tensor work and twice the TMEM reads; 527 us at B=128, S=576, H=16.)
 //
 // One persistent CTA per SM; work unit = (sample, head, pair of 128-row query tiles); keys in blocks of 192:
-//   warp 0   TMA: Q pair (256 x 128 B box, 2-deep), K / V blocks (192 x 128 B boxes) through a 4-stage ring in consumption order
-//            (pass A: K_0..K_n-1; pass B: K_0, V_0, K_1, V_1, ...)
+//   warp 0   TMA: Q pair (256 x 128 B box, 2-deep), K / V blocks (192 x 128 B boxes) through a 4-stage ring: K_0, V_0, K_1, V_1, ...
 //   warp 1   MMA issuer (tcgen05.mma: S_t = Q_t K_j^T, SS, N = 192; O_t += P_t V_j, A from TMEM, B MN-major, N = 64)
 //   warp 2   TMEM allocator: query tile t owns columns [256t, 256t+256): S [0,192) / P [0,96) / O [192,256)
 //   warps 4-11  softmax + output, 4 warps per query tile, thread = query row
@@ -49,8 +51,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint64_t* q_full = bars + 2 * ATL_NST; // [2]
   uint64_t* q_empty = q_full + 2;        // [2]
   uint64_t* s_full = q_empty + 2;        // [2] per query tile
-  uint64_t* s_free = s_full + 2;         // [2]
-  uint64_t* p_ready = s_free + 2;        // [2]
+  uint64_t* pv_done = s_full + 2;        // [2] every P V block (only waited on by the rare O rescale)
+  uint64_t* p_ready = pv_done + 2;       // [2]
   uint64_t* o_full = p_ready + 2;        // [2]
   uint64_t* o_free = o_full + 2;         // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 2);
@@ -73,7 +75,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);
+      mbar_init(&pv_done[i], 1);
       mbar_init(&p_ready[i], 4);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 4);
@@ -102,14 +104,12 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         mbar_wait(&q_empty[qb], ((ui >> 1) & 1) ^ 1);
         mbar_arrive_expect_tx(&q_full[qb], ATL_Q_BYTES);
         tma_load_2d(smem_q + qb * ATL_Q_BYTES, &map_q, &q_full[qb], h * 64, row0 + qp * 256);
-        for (int pass = 0; pass < 2; ++pass) {
-          for (int j = 0; j < p.n_blk; ++j) {
-            for (int kv = 0; kv <= pass; ++kv) {  // pass A: K only; pass B: K then V
-              mbar_wait(&kv_empty[st], st_ph ^ 1);
-              mbar_arrive_expect_tx(&kv_full[st], ATL_KV_BYTES);
-              tma_load_2d(smem_kv + st * ATL_KV_BYTES, &map_kv, &kv_full[st], (kv + 1) * p.D + h * 64, row0 + j * ATL_KB);
-              if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
-            }
+        for (int j = 0; j < p.n_blk; ++j) {
+          for (int kv = 0; kv < 2; ++kv) {  // K_j then V_j
+            mbar_wait(&kv_empty[st], st_ph ^ 1);
+            mbar_arrive_expect_tx(&kv_full[st], ATL_KV_BYTES);
+            tma_load_2d(smem_kv + st * ATL_KV_BYTES, &map_kv, &kv_full[st], (kv + 1) * p.D + h * 64, row0 + j * ATL_KB);
+            if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
           }
         }
       }
@@ -121,7 +121,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);
       int st = 0;
       uint32_t st_ph = 0;
-      uint32_t n_sfree[2] = {0, 0}, n_pready[2] = {0, 0}, n_used[2] = {0, 0};
+      uint32_t n_pready[2] = {0, 0}, n_used[2] = {0, 0};
       int ui = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
         const int ue = p.reverse ? num_units - 1 - unit : unit;
@@ -131,13 +131,13 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t q_addr = smem_u32(smem_q + qb * ATL_Q_BYTES);
         mbar_wait(&q_full[qb], (ui >> 1) & 1);
         tcgen05_fence_after();
-        // ---- pass A: S blocks for the row maxima ----
         for (int j = 0; j < p.n_blk; ++j) {
+          // S_t = Q_t K_j^T.  The S / P columns are free: the previous block's P V was issued after the softmax warps had
+          // finished with them, and the tensor pipe executes in issue order.
           mbar_wait(&kv_full[st], st_ph);
           tcgen05_fence_after();
           const uint32_t k_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
           for (int t = 0; t < nq; ++t) {
-            if (j > 0) { mbar_wait(&s_free[t], n_sfree[t] & 1); ++n_sfree[t]; tcgen05_fence_after(); }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
@@ -146,22 +146,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           }
           tcgen05_commit(&kv_empty[st]);
           if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
-        }
-        // ---- pass B: S -> P -> O += P V ----
-        for (int j = 0; j < p.n_blk; ++j) {
-          mbar_wait(&kv_full[st], st_ph);
-          tcgen05_fence_after();
-          const uint32_t k_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
-          for (int t = 0; t < nq; ++t) {
-            if (j == 0) { mbar_wait(&s_free[t], n_sfree[t] & 1); ++n_sfree[t]; tcgen05_fence_after(); }  // last pass-A block was read
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
-                         k > 0 ? 1u : 0u);
-            tcgen05_commit(&s_full[t]);
-          }
-          tcgen05_commit(&kv_empty[st]);
-          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+          // O_t += P_t V_j
           mbar_wait(&kv_full[st], st_ph);
           tcgen05_fence_after();
           const uint32_t v_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
@@ -174,6 +159,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             for (int kk = 0; kk < ATL_KB / 16; ++kk)
               umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
                           (j | kk) != 0 ? 1u : 0u);
+            tcgen05_commit(&pv_done[t]);
             if (j == p.n_blk - 1) tcgen05_commit(&o_full[t]);
           }
           tcgen05_commit(&kv_empty[st]);
@@ -188,7 +174,8 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     const int q = warp_idx & 3;
     const int t = (warp_idx - 4) >> 2;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
-    uint32_t n_sfull = 0, n_ofull = 0;
+    uint32_t n_sfull = 0, n_ofull = 0, n_pv = 0;  // n_pv: P V blocks issued for this tile so far (phases of pv_done)
+    constexpr int PT = FMT == 0 ? 1 : 2;
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int ue = p.reverse ? num_units - 1 - unit : unit;
       const int qp = ue % p.n_qp, bh = ue / p.n_qp;
@@ -196,8 +183,10 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const int nq = (S - qp * 256 > 128) ? 2 : 1;
       if (t >= nq) continue;
       const int row = qp * 256 + t * 128 + q * 32 + lane;
-      // ---- pass A: row max over all key blocks ----
-      float m = -INFINITY;
+      float ms = -INFINITY;  // reference maximum, already multiplied by scale_log2
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      float2 mo2 = make_float2(0.f, 0.f);
+      float2 l2 = make_float2(0.f, 0.f);
       uint32_t r[32], rn[32];
       for (int j = 0; j < p.n_blk; ++j) {
         const int kvalid = min(ATL_KB, S - j * ATL_KB);   // valid keys in this block (only the last block is partial)
@@ -205,41 +194,53 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         mbar_wait(&s_full[t], n_sfull & 1);
         ++n_sfull;
         tcgen05_fence_after();
-        auto max_chunk = [&](const uint32_t (&sv)[32], int c) {
+        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
+          // chunk maximum; raise the reference only when it is exceeded by more than 8 (log2 domain)
+          float cm = -INFINITY;
           if (c < n_full) {
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 2) m = fmax3(m, __uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1]));
+            for (int jj = 0; jj < 32; jj += 2) cm = fmax3(cm, __uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1]));
           } else {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) m = (c * 32 + jj < kvalid) ? fmaxf(m, __uint_as_float(sv[jj])) : m;
+            for (int jj = 0; jj < 32; ++jj) cm = (c * 32 + jj < kvalid) ? fmaxf(cm, __uint_as_float(sv[jj])) : cm;
           }
-        };
-        tmem_ld_32x32b_x32(taddr, r);
-        for (int c = 0; c < n_live; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
-          max_chunk(r, c);
-          if (c + 1 < n_live) {
-            tmem_ld_wait();
-            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
-            max_chunk(rn, c + 1);
+          const float cs = cm * p.scale_log2;
+          const bool raise = cs > ms + 8.0f;
+          if (__any_sync(0xffffffffu, raise)) {
+            // rare: rescale what this row has accumulated under the old reference (lanes that do not raise use factor 1)
+            const float f = raise ? ex2_approx(ms - cs) : 1.0f;
+            l2.x *= f;
+            l2.y *= f;
+            for (int cc = 0; cc < c; ++cc) {  // P chunks of this block already written
+              uint32_t pk[16];
+              tmem_ld_32x32b_x16(taddr + cc * 16, pk);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) {
+                float2 v;
+                if (PT == 1) v = __half22float2(*reinterpret_cast<const __half2*>(&pk[jj]));
+                else v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[jj]));
+                pk[jj] = pack2(v.x * f, v.y * f, PT);
+              }
+              tmem_st_32x32b_x16(taddr + cc * 16, pk);
+            }
+            if (j > 0) {  // O accumulated over the previous blocks: wait for the last P V, scale in place
+              mbar_wait(&pv_done[t], (n_pv - 1) & 1);
+              tcgen05_fence_after();
+#pragma unroll
+              for (int oc = 0; oc < 4; ++oc) {
+                uint32_t ov[16];
+                tmem_ld_32x32b_x16(taddr + 192 + oc * 16, ov);
+                tmem_ld_wait();
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) ov[jj] = __float_as_uint(__uint_as_float(ov[jj]) * f);
+                tmem_st_32x32b_x16(taddr + 192 + oc * 16, ov);
+              }
+            }
+            tmem_st_wait();
+            if (raise) ms = cs;
+            mo2 = make_float2(-ms, -ms);
           }
-        }
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);
-      }
-      // ---- pass B: P blocks (the MMA warp accumulates O) ----
-      const float moff = m * p.scale_log2;
-      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2), mo2 = make_float2(-moff, -moff);
-      float2 l2 = make_float2(0.f, 0.f);
-      for (int j = 0; j < p.n_blk; ++j) {
-        const int kvalid = min(ATL_KB, S - j * ATL_KB);
-        const int n_live = (kvalid + 31) / 32, n_full = kvalid / 32;
-        mbar_wait(&s_full[t], n_sfull & 1);
-        ++n_sfull;
-        tcgen05_fence_after();
-        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
           uint32_t pk[16];
 #pragma unroll
           for (int jj = 0; jj < 32; jj += 2) {
@@ -250,7 +251,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
               e.y = (c * 32 + jj + 1 < kvalid) ? e.y : 0.f;
             }
             l2 = fadd2(l2, e);
-            pk[jj >> 1] = pack2(e.x, e.y, FMT == 0 ? 1 : 2);
+            pk[jj >> 1] = pack2(e.x, e.y, PT);
           }
           tmem_st_32x32b_x16(taddr + c * 16, pk);
         };
@@ -275,6 +276,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[t]);
+        ++n_pv;
       }
       // ---- output ----
       const float inv = 1.0f / (l2.x + l2.y);

@@ -190,7 +190,7 @@ def test_attention_many_items_persistent(lib):
 
 
 def test_attention_long_many_units_persistent(lib):
-    """S > 256: two-pass tcgen05 kernel; more units than SMs, partial last key block and single-tile last query pair."""
+    """S > 256: key-block tcgen05 kernel; more units than SMs, partial last key block and single-tile last query pair."""
     B, S, H = 24, 576, 4
     qkv = (torch.randn(B * S, 3 * H * 64, device=DEV)).half()
     out = torch.empty(B * S, H * 64, dtype=torch.float16, device=DEV)
@@ -198,10 +198,11 @@ def test_attention_long_many_units_persistent(lib):
     assert rel_err(out, _attn_ref(qkv, B, S, H, 0)) < 3e-3
 
 
-@pytest.mark.parametrize("S", [197, 256])
+@pytest.mark.parametrize("S", [197, 256, 300, 576, 1024])
 def test_attention_lazy_rescale_path(lib, S):
     """Scores that keep growing along the key axis force the lazily raised reference maximum (and the rescale of the P chunks
-    already written to tensor memory) at every 32-key chunk of the single-pass softmax."""
+    already written to tensor memory -- for S > 256 also of the O accumulator, across key blocks) at every 32-key chunk of the
+    single-pass softmax."""
     B, H = 2, 2
     g = torch.Generator(device="cpu").manual_seed(3)
     q = torch.randn(B, S, H, 64, generator=g)
