@@ -299,6 +299,22 @@ def run_ours(args):
         step_host()
     ms_e2e, out_h = timed(step_host, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    # the same loop with asynchronous dispatch, two calls in flight (every step still copies its inputs in and its result out)
+    pipelined = None
+    if not dual and hasattr(model, "forward_async"):
+        state = {"pending": None}
+
+        def step_async():
+            nxt = model.forward_async(img_host)
+            out = state["pending"].result() if state["pending"] is not None else None
+            state["pending"] = nxt
+            return out
+
+        for _ in range(2):
+            step_async()
+        ms_pipe, _ = timed(step_async, args.steps)
+        state["pending"].result()
+        pipelined = world * B * args.steps / (ms_pipe * 1e-3)
     h2d = img_host.numel() * 4 + (ids_host.numel() * 4 if dual else 0)
     d2h = out_h.numel() * 4
 
@@ -323,7 +339,8 @@ def run_ours(args):
                        "l2_policy": "inputs_larger_than_L2 (154 MB fp32 images; >1 GB of activations streamed per step)",
                        "gflop_per_image": gflop},
             "model_tflops": value * gflop / 1e3, "model_frac_of_peak": value * gflop / 1e3 / (peak_tf * world),
-            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "sync": "every step (value above)", "pipelined_depth2_value": pipelined},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

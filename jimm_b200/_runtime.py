@@ -29,6 +29,22 @@ def _as_tensor(x, what: str) -> torch.Tensor:
     return torch.as_tensor(np.asarray(x))
 
 
+class PendingResult:
+    """Result of an asynchronously dispatched forward: `.result()` waits for that call's work only."""
+
+    def __init__(self, tensor: torch.Tensor, event, keep=None):
+        self._tensor, self._event, self._keep = tensor, event, keep
+
+    def done(self) -> bool:
+        return self._event is None or self._event.query()
+
+    def result(self) -> torch.Tensor:
+        if self._event is not None:
+            self._event.synchronize()
+            self._event = self._keep = None
+        return self._tensor
+
+
 class NativeModel:
     """One opaque jimm_model_t on one GPU."""
 
@@ -108,11 +124,26 @@ class NativeModel:
                 _lib.check(fn_dev(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(out.data_ptr()),
                                   C.c_void_p(_stream_ptr(self.device))))
             return out
+        return self._vision_host(x, encode).result()
+
+    def vision_async(self, x, encode: bool = False) -> "PendingResult":
+        """Host input: enqueue H2D + forward + D2H and return without synchronising (JAX-style asynchronous dispatch);
+        `.result()` waits for this call only.  Back-to-back calls pipeline: the copies of call k+1 run under the towers of
+        call k.  The caller keeps `x` alive and unmodified until the result is taken."""
+        x = self._prep_images(x)
+        if x.is_cuda:
+            return PendingResult(self.vision(x, encode), None)
+        return self._vision_host(x, encode)
+
+    def _vision_host(self, x: torch.Tensor, encode: bool) -> "PendingResult":
+        B = x.shape[0]
+        fn_dev = self.lib.jimm_encode_image if encode else self.lib.jimm_vit_forward
         # host path: H2D + forward + D2H enqueued by the library on the current stream
         with torch.cuda.device(self.device):
             # fresh pinned result (torch's caching host allocator makes this cheap); no CPU-side tensor op on this path: an
             # intra-op OpenMP team on a CPU-quota-limited box costs milliseconds
             out = torch.empty((B, self.vision_out), dtype=torch.float32, pin_memory=True)
+            cur = torch.cuda.current_stream(self.device)
             if encode:
                 xd = x.to(self.device, non_blocking=True)
                 od = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
@@ -122,8 +153,9 @@ class NativeModel:
             else:
                 _lib.check(self.lib.jimm_vit_forward_host(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B,
                                                           C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
-            torch.cuda.current_stream(self.device).synchronize()
-        return out
+            ev = torch.cuda.Event()
+            ev.record(cur)
+        return PendingResult(out, ev, keep=x)
 
     def text(self, ids) -> torch.Tensor:
         ids = self._prep_ids(ids)

@@ -130,3 +130,8 @@ class VisionTransformerBase(_NativeOwner, nn.Module):
         """[batch, height, width, channels] -> [batch, hidden_size] (CLS token or MAP head output)."""
         B = img.shape[0]
         return self.native(B).vision(img)
+
+    def forward_async(self, img):
+        """Asynchronous dispatch for host inputs (the reference's calls return before the device finishes, examples/vit_inference.py:54
+        only blocks when it reads the logits): returns a `PendingResult`; back-to-back calls overlap their copies with compute."""
+        return self.native(img.shape[0]).vision_async(img)

@@ -183,6 +183,12 @@ struct jimm_model {
   cudaEvent_t ev_copied[kHostSlices] = {};
   cudaEvent_t ev_consumed[kHostSlices] = {};
   cudaEvent_t ev_start = nullptr;
+  // Back-to-back host-path calls on one stream are ordered slot by slot (a slot is free again once its slice has been through
+  // patchify), so the copies of call k+1 run under the towers of call k: the asynchronous-dispatch pipeline of the reference.
+  bool host_chain = false;            // the last toucher of the staging buffer was jimm_vit_forward_host ...
+  cudaStream_t host_chain_stream = nullptr;  // ... on this stream ...
+  int host_chain_sizes[kHostSlices] = {};    // ... with this slice layout
+  bool slot_recorded[kHostSlices] = {};
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
   size_t prof_used = 0;
@@ -554,7 +560,10 @@ static int run_graphed(jimm_model* m, std::tuple<int, int, int> key, cudaStream_
 static int exec_vision(jimm_model* m, const void* img, int in_dtype, int n, float* out, cudaStream_t s) {
   if (n <= 0 || n > m->graph_max_batch || !m->graph_out) return run_vision(m, img, in_dtype, n, out, s);
   const size_t bytes = static_cast<size_t>(n) * m->vis.img * m->vis.img * m->vis.C * dtype_size(in_dtype);
-  if (img != m->ws.in_img) JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, img, bytes, cudaMemcpyDeviceToDevice, s));
+  if (img != m->ws.in_img) {
+    m->host_chain = false;  // the staging buffer is written outside the host path's slot protocol
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_img, img, bytes, cudaMemcpyDeviceToDevice, s));
+  }
   JIMM_TRY(run_graphed(m, std::make_tuple(0, n, in_dtype), s, [&](cudaStream_t cs) { return run_vision(m, m->ws.in_img, in_dtype, n, m->graph_out, cs); }));
   JIMM_CUDA_CHECK(cudaMemcpyAsync(out, m->graph_out, static_cast<size_t>(n) * vision_out_dim(m) * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
@@ -984,27 +993,34 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
   // Sliced pipeline per super-chunk of <= max_batch images: slice i+1 is copied on the side stream while slice i is in the
   // tower, and the next super-chunk's first copy overlaps this one's last forward.  The slices partition the staging buffer
   // (max_batch fp32 images), one event pair each; one D2H of the super-chunk's result at its end.
-  JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));  // earlier work on the caller's stream may still read the staging slots
-  JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-  int uses[jimm_model::kHostSlices] = {};
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
     int sizes[jimm_model::kHostSlices];
     host_slices(m, nb, sizes);
+    bool same_layout = m->host_chain && m->host_chain_stream == s;
+    for (int i = 0; i < jimm_model::kHostSlices; ++i) same_layout = same_layout && sizes[i] == m->host_chain_sizes[i];
+    if (!same_layout) {
+      // earlier work on the caller's stream may still read the staging buffer in another layout: order the copies after all of it
+      JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
+      JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
+      for (int i = 0; i < jimm_model::kHostSlices; ++i) { m->slot_recorded[i] = false; m->host_chain_sizes[i] = sizes[i]; }
+      m->host_chain = true;
+      m->host_chain_stream = s;
+    }
     int off = 0;
     for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
       const int n = sizes[slot];
       if (n <= 0) continue;
       uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
       float* out_d = m->ws.out_dev + static_cast<size_t>(off) * od;
-      if (uses[slot] > 0) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
+      if (m->slot_recorded[slot]) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
       JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + static_cast<size_t>(b0 + off) * img_bytes, n * img_bytes,
                                       cudaMemcpyHostToDevice, m->copy_stream));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
       JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
       JIMM_TRY(exec_vision(m, dst, in_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
-      ++uses[slot];
+      m->slot_recorded[slot] = true;
       off += n;
     }
     JIMM_CUDA_CHECK(cudaMemcpyAsync(out_host + static_cast<size_t>(b0) * od, m->ws.out_dev, static_cast<size_t>(nb) * od * sizeof(float),
@@ -1032,6 +1048,7 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
   // JIMM_HOST_SLICES asks otherwise.
   // The token ids go first: H2D copies share one copy engine, so ids submitted after the images would queue behind them and
   // hold the text tower back.
+  m->host_chain = false;
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
   JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids_host, static_cast<size_t>(Bt) * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));

@@ -49,6 +49,11 @@ class VisionTransformer(_NativeOwner, nn.Module):
         Inference semantics (dropout is the identity), like the reference after `.eval()`."""
         return self.native(x.shape[0]).vision(x)
 
+    def forward_async(self, x):
+        """Asynchronous dispatch for host inputs (JAX dispatches asynchronously; examples/vit_inference.py:54-58 only blocks when
+        it reads the logits): returns a `PendingResult`; back-to-back calls overlap their H2D copies with the previous forward."""
+        return self.native(x.shape[0]).vision_async(x)
+
     @classmethod
     def from_pretrained(cls, model_name_or_path: str, use_pytorch: bool = False, mesh=None, dtype=torch.float32) -> "VisionTransformer":
         """Load a HF `ViTForImageClassification` checkpoint (models/vit.py:105-273): same config parsing, shape

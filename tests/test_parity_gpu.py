@@ -385,3 +385,23 @@ def test_small_batch_graph_replay_dual():
     for _ in range(3):
         assert torch.equal(m.encode_text(txt[:3].contiguous()), full[:3])
         assert torch.equal(m.encode_text(txt[:, :11].contiguous()), m.encode_text(txt[:, :11].contiguous()))
+
+
+def test_async_host_pipeline(vitb16):
+    """forward_async: several host batches in flight (slot-by-slot ordering of the staging buffer across calls) return the same
+    bits as synchronous calls, whatever mix of batch sizes, and interleave safely with device-input calls."""
+    from jimm_b200.models import VisionTransformer
+
+    cfg, p, img, ref = vitb16
+    m = _set(VisionTransformer(dtype=torch.float16), p).eval().set_max_batch(160)
+    big = O.synthetic_images(160, 224, seed=21)
+    xs = [big.pin_memory(), torch.flip(big, dims=[0]).contiguous().pin_memory(), big[:130].contiguous().pin_memory(), img.pin_memory()]
+    sync = [m(x) for x in xs]
+    assert rel(sync[3], ref) < TOL
+    pend = [m.forward_async(x) for x in (xs[0], xs[1], xs[0], xs[2], xs[3], xs[1])]
+    dev_out = m(big.cuda())  # device-input call queued behind the host calls on the same stream
+    outs = [q.result() for q in pend]
+    for o, k in zip(outs, (0, 1, 0, 2, 3, 1)):
+        assert not o.is_cuda and torch.equal(o, sync[k])
+    assert torch.equal(dev_out.cpu(), sync[0])
+    assert torch.equal(sync[1], torch.flip(sync[0], dims=[0]))
