@@ -70,10 +70,11 @@ class CLIP(DualTower):
             else:
                 raise ValueError(f"Configuration could not be loaded for PyTorch model {model_name_or_path}")
         tc, vc = config["text_config"], config["vision_config"]
-        model = cls(image_resolution=vc["image_size"], vision_layers=vc["num_hidden_layers"], vision_width=vc["hidden_size"],
-                    vision_patch_size=vc["patch_size"], context_length=tc["max_position_embeddings"], vocab_size=tc["vocab_size"],
-                    transformer_width=tc["hidden_size"], transformer_heads=tc["num_attention_heads"],
-                    transformer_layers=tc["num_hidden_layers"], mesh=mesh, dtype=dtype, param_dtype=dtype)
+        with nn.deferred_init():  # every parameter is overwritten below (and asserted to be)
+            model = cls(image_resolution=vc["image_size"], vision_layers=vc["num_hidden_layers"], vision_width=vc["hidden_size"],
+                        vision_patch_size=vc["patch_size"], context_length=tc["max_position_embeddings"], vocab_size=tc["vocab_size"],
+                        transformer_width=tc["hidden_size"], transformer_heads=tc["num_attention_heads"],
+                        transformer_layers=tc["num_hidden_layers"], mesh=mesh, dtype=dtype, param_dtype=dtype)
         flax_params = model.flat_params()
         mapping = {
             "logit_scale": "logit_scale",

@@ -57,10 +57,11 @@ class SigLIP(DualTower):
         for k in params_fstate:
             if k.startswith("text_model.encoder.layers.") and k.endswith(".self_attn.q_proj.weight"):
                 text_num_layers = max(text_num_layers, int(k.split(".")[3]) + 1)
-        model = cls(image_resolution=config["vision_config"]["image_size"], vision_layers=vision_num_layers, vision_width=vision_width,
-                    vision_patch_size=vision_patch_size, context_length=context_length, vocab_size=vocab_size,
-                    transformer_width=text_hidden, transformer_heads=text_hidden // 64, transformer_layers=text_num_layers, mesh=mesh,
-                    dtype=dtype, param_dtype=dtype)
+        with nn.deferred_init():  # every parameter is overwritten below (and asserted to be)
+            model = cls(image_resolution=config["vision_config"]["image_size"], vision_layers=vision_num_layers, vision_width=vision_width,
+                        vision_patch_size=vision_patch_size, context_length=context_length, vocab_size=vocab_size,
+                        transformer_width=text_hidden, transformer_heads=text_hidden // 64, transformer_layers=text_num_layers, mesh=mesh,
+                        dtype=dtype, param_dtype=dtype)
         flax_params = model.flat_params()
         v_, m_ = "vision_model.", "vision_model.MAPHead."
         mapping = {

@@ -88,9 +88,10 @@ class VisionTransformer(_NativeOwner, nn.Module):
         else:
             raise ValueError(f"Could not load or infer configuration for {model_name_or_path}")
 
-        model = cls(num_classes=num_classes_val, img_size=img_size_val, patch_size=patch_size_val, num_layers=num_layers_val,
-                    num_heads=num_heads_val, mlp_dim=mlp_dim_val, hidden_size=hidden_size_val, use_quick_gelu=use_quick_gelu_val,
-                    mesh=mesh, dtype=dtype, param_dtype=dtype)
+        with nn.deferred_init():  # every parameter is overwritten below (and asserted to be)
+            model = cls(num_classes=num_classes_val, img_size=img_size_val, patch_size=patch_size_val, num_layers=num_layers_val,
+                        num_heads=num_heads_val, mlp_dim=mlp_dim_val, hidden_size=hidden_size_val, use_quick_gelu=use_quick_gelu_val,
+                        mesh=mesh, dtype=dtype, param_dtype=dtype)
         flax_params = model.flat_params()
 
         def hf_param_name(name: str) -> str:
