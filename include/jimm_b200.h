@@ -159,6 +159,9 @@ JIMM_API int jimm_k_resample_coeffs(int in_size, int out_size, int resample, int
  * argmax (nullable, int32 [rows]): first maximum per row (examples/vit_inference.py:58).  order / argmax need cols <= 4096. */
 JIMM_API int jimm_postprocess(const float* logits, int rows, int cols, int ld, int mode, float* probs, int ldp, int32_t* order, int32_t* argmax,
                               void* stream);
+/* Micro-benchmark (not on the product path): TMA fill bandwidth from L2 with `cluster` CTAs per cluster.  mode 0: every CTA loads
+ * its own 16 KB tiles; 1: the CTAs of a cluster load the same tile each; 2: same tile, each loads 1/cluster of it and multicasts. */
+JIMM_API int jimm_k_l2_probe(const void* buf, int rows, int mode, int cluster, int iters, float* ms, void* stream);
 /* Live timing of the dominant kernel (the tcgen05 GEMM) inside a forward: between begin and end every GEMM launch is
  * bracketed by CUDA events on the launch stream; end synchronises and returns the summed device time (ms), the
  * algorithmic FLOPs (2*M*N*K per launch) and the number of launches.  Used by bench.py's roofline object. */
