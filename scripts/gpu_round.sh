@@ -11,6 +11,7 @@ for s in $STAGES; do
     kernels) timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 300 > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" ;;
     kernels_all) timeout 900 python -m pytest tests/test_kernels_gpu.py -q -m gpu --timeout 300 > gpurun_out/kernels.log 2>&1; echo "kernels rc=$?" ;;
     parity)  timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu --timeout 600 > gpurun_out/parity.log 2>&1; echo "parity rc=$?" ;;
+    alltests) timeout 1500 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/alltests.log 2>&1; echo "alltests rc=$?"; tail -n 6 gpurun_out/alltests.log ;;
     smoke)   timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" ;;
     bench)   timeout 600 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" ;;
     benchref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err; echo "benchref rc=$?" ;;
