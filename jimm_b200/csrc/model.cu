@@ -1003,7 +1003,12 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
       // earlier work on the caller's stream may still read the staging buffer in another layout: order the copies after all of it
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
       JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-      for (int i = 0; i < jimm_model::kHostSlices; ++i) { m->slot_recorded[i] = false; m->host_chain_sizes[i] = sizes[i]; }
+      for (int i = 0; i < jimm_model::kHostSlices; ++i) {
+        // ... and after the slices of an earlier host call, which may have run on another stream
+        if (m->slot_recorded[i]) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[i], 0));
+        m->slot_recorded[i] = false;
+        m->host_chain_sizes[i] = sizes[i];
+      }
       m->host_chain = true;
       m->host_chain_stream = s;
     }
