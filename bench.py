@@ -30,7 +30,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GFLOP_PER_IMG = {"vit_b16": 35.128, "vit_l16_map": 383.85, "clip_b32": 14.778, "siglip_b16": 57.85}
+GFLOP_PER_IMG = {"vit_b16": 35.128, "vit_l16_map": 383.85, "clip_b32": 14.778, "siglip_b16": 57.85, "siglip2_l16_512": 766.55}
 
 WORKLOADS = {
     # name: (description, per-GPU batch, dtype)
@@ -38,6 +38,8 @@ WORKLOADS = {
     "vit_l16_map": ("ViT-L/16 @384 MAP head, batch 128/GPU, bf16 operands (BASELINE configs[2])", 128, "bfloat16"),
     "clip_b32": ("CLIP ViT-B/32 dual tower, batch 256 pairs/GPU, fp16 (BASELINE configs[3])", 256, "float16"),
     "siglip_b16": ("SigLIP-B/16 @256 dual tower, batch 256 pairs/GPU, fp16 (north-star extra)", 256, "float16"),
+    "siglip2_l16_512": ("SigLIP2-L/16 @512 dual tower (S=1024), batch 256 pairs/GPU, bf16, vocab 32000 stand-in (BASELINE configs[4] per-GPU share)",
+                        256, "bfloat16"),
 }
 
 
@@ -119,6 +121,10 @@ def build_model(workload: str, dtype_name: str):
         return CLIP(224, 12, 768, 32, 77, 49408, 512, 8, 12, dtype=dt, rngs=Rngs(0)), 224, (77, 49408, "clip")
     if workload == "siglip_b16":
         return SigLIP(256, 12, 768, 16, 64, 32000, 768, 12, 12, dtype=dt, rngs=Rngs(0)), 256, (64, 32000, "siglip")
+    if workload == "siglip2_l16_512":
+        # vision 1024/24L/16H patch 16 @512 (S = 1024, MAP head), text 1024/24L/16H/T64; the embedding gather
+        # does not depend on the vocabulary size, 32000 keeps the random init short
+        return SigLIP(512, 24, 1024, 16, 64, 32000, 1024, 16, 24, dtype=dt, rngs=Rngs(0)), 512, (64, 32000, "siglip")
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -165,6 +171,11 @@ def oracle_step_fn(workload: str, B: int):
         p = O.random_dual_params(cfg, "clip", seed=0)
         img, txt = O.synthetic_images(B, 224), O.synthetic_tokens(B, 77, 49408, "clip")
         return lambda: O.clip_forward(p, cfg, img, txt)
+    if workload == "siglip2_l16_512":
+        cfg = O.DualCfg(512, 24, 1024, 16, 64, 32000, 1024, 16, 24)
+        p = O.random_dual_params(cfg, "siglip", seed=0)
+        img, txt = O.synthetic_images(B, 512), O.synthetic_tokens(B, 64, 32000, "siglip")
+        return lambda: O.siglip_forward(p, cfg, img, txt)
     cfg = O.DualCfg(256, 12, 768, 16, 64, 32000, 768, 12, 12)
     p = O.random_dual_params(cfg, "siglip", seed=0)
     img, txt = O.synthetic_images(B, 256), O.synthetic_tokens(B, 64, 32000, "siglip")

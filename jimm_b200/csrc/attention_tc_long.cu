@@ -12,8 +12,12 @@
 // One persistent CTA per SM; work unit = (sample, head, pair of 128-row query tiles); keys in blocks of 192:
 //   warp 0   TMA: Q pair (256 x 128 B box, 2-deep), K / V blocks (192 x 128 B boxes) through a 4-stage ring: K_0, V_0, K_1, V_1, ...
 //   warp 1   MMA issuer (tcgen05.mma: S_t = Q_t K_j^T, SS, N = 192; O_t += P_t V_j, A from TMEM, B MN-major, N = 64)
-//   warp 2   TMEM allocator: query tile t owns columns [256t, 256t+256): S [0,192) / P [0,96) / O [192,256)
-//   warps 4-11  softmax + output, 4 warps per query tile, thread = query row
+//   warp 2   TMEM allocator: query tile t owns columns [256t, 256t+256): S [0,192) / P [0,48) + [96,144) / O [192,256)
+//   warps 4-19  softmax + output: 8 warps per query tile = 4 lane quarters x 2 halves of the 192 score columns, so every SM
+//            sub-partition holds four softmax warps (the phase is MUFU-bound; two warps per sub-partition left it latency-bound:
+//            332 us at B=32 S=1024 H=16).  The two warps of a row agree on the reference maximum once per key block through shared
+//            memory (each first takes the maximum of its 96 columns -- a second, cheap read of tensor memory), so the raise
+//            decision is taken before any P of the block is written and only the running sums and the O accumulator need rescaling.
 #include <type_traits>
 
 #include "common.cuh"
@@ -21,12 +25,13 @@
 
 namespace jimm {
 
-static constexpr int ATL_THREADS = 384;
+static constexpr int ATL_THREADS = 640;
 static constexpr int ATL_KB = 192;                          // keys per block
 static constexpr int ATL_Q_BYTES = 256 * 128;               // Q pair box
 static constexpr int ATL_KV_BYTES = ATL_KB * 128;           // K or V block box
 static constexpr int ATL_NST = 4;                           // K/V ring stages
-static constexpr int ATL_SMEM = 2 * ATL_Q_BYTES + ATL_NST * ATL_KV_BYTES + 512 + 1024;
+static constexpr int ATL_XCH_BYTES = 2 * 128 * 2 * 4;  // [tile][row][column half] floats exchanged between the two warps of a row
+static constexpr int ATL_SMEM = 2 * ATL_Q_BYTES + ATL_NST * ATL_KV_BYTES + 512 + ATL_XCH_BYTES + 1024;
 
 struct AtlParams {
   int B, S, H, D;
@@ -56,6 +61,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
   uint64_t* o_full = p_ready + 2;        // [2]
   uint64_t* o_free = o_full + 2;         // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_free + 2);
+  float* xch = reinterpret_cast<float*>(smem + 2 * ATL_Q_BYTES + ATL_NST * ATL_KV_BYTES + 512);  // [2][128][2]
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_units = p.B * p.H * p.n_qp;
@@ -76,9 +82,9 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       mbar_init(&q_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&p_ready[i], 4);
+      mbar_init(&p_ready[i], 8);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_free[i], 4);
+      mbar_init(&o_free[i], 8);
     }
     fence_barrier_init();
   }
@@ -131,39 +137,53 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t q_addr = smem_u32(smem_q + qb * ATL_Q_BYTES);
         mbar_wait(&q_full[qb], (ui >> 1) & 1);
         tcgen05_fence_after();
-        for (int j = 0; j < p.n_blk; ++j) {
-          // S_t = Q_t K_j^T.  The S / P columns are free: the previous block's P V was issued after the softmax warps had
-          // finished with them, and the tensor pipe executes in issue order.
-          mbar_wait(&kv_full[st], st_ph);
-          tcgen05_fence_after();
-          const uint32_t k_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
-          for (int t = 0; t < nq; ++t) {
+        auto issue_qk = [&](int t, uint32_t k_addr) {
+          // S_t = Q_t K^T.  The S / P columns of tile t are free: its previous P V was issued after the softmax warps had finished with
+          // them, and the tensor pipe executes in issue order.
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
-                         k > 0 ? 1u : 0u);
-            tcgen05_commit(&s_full[t]);
-          }
-          tcgen05_commit(&kv_empty[st]);
-          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
-          // O_t += P_t V_j
-          mbar_wait(&kv_full[st], st_ph);
-          tcgen05_fence_after();
-          const uint32_t v_addr = smem_u32(smem_kv + st * ATL_KV_BYTES);
+          for (int k = 0; k < 4; ++k)
+            umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
+                       k > 0 ? 1u : 0u);
+          tcgen05_commit(&s_full[t]);
+        };
+        auto next_stage = [&]() { if (++st == ATL_NST) { st = 0; st_ph ^= 1; } };
+        // prologue: scores of block 0 for both tiles
+        mbar_wait(&kv_full[st], st_ph);
+        tcgen05_fence_after();
+        for (int t = 0; t < nq; ++t) issue_qk(t, smem_u32(smem_kv + st * ATL_KV_BYTES));
+        tcgen05_commit(&kv_empty[st]);
+        next_stage();
+        for (int j = 0; j < p.n_blk; ++j) {
+          // Per tile: O_t += P_t V_j as soon as ITS softmax is done, immediately followed by ITS next scores S_t = Q_t K_{j+1}^T -- the
+          // other tile's softmax overlaps these MMAs (issuing both tiles' scores together, as before, made the tiles run in lock-step:
+          // every softmax warp then waited for the whole MMA phase, 30 % of all stall samples).
+          const int sv = st;
+          const uint32_t phv = st_ph;  // V_j
+          next_stage();
+          const bool more = j + 1 < p.n_blk;
+          const int sk = st;
+          const uint32_t phk = st_ph;  // K_{j+1} (only when `more`)
+          if (more) next_stage();
+          const uint32_t v_addr = smem_u32(smem_kv + sv * ATL_KV_BYTES), k_addr = smem_u32(smem_kv + sk * ATL_KV_BYTES);
           for (int t = 0; t < nq; ++t) {
             mbar_wait(&p_ready[t], n_pready[t] & 1);
             ++n_pready[t];
             if (j == 0 && n_used[t] > 0) mbar_wait(&o_free[t], (n_used[t] - 1) & 1);  // previous unit's O of this tile was read out
+            if (t == 0) mbar_wait(&kv_full[sv], phv);
             tcgen05_fence_after();
 #pragma unroll
             for (int kk = 0; kk < ATL_KB / 16; ++kk)
-              umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
-                          (j | kk) != 0 ? 1u : 0u);
+              umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + (kk < ATL_KB / 32 ? kk * 8 : 96 + (kk - ATL_KB / 32) * 8),
+                          make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0 ? 1u : 0u);  // P: keys 0-95 at columns 0-47, keys 96-191 at 96-143
             tcgen05_commit(&pv_done[t]);
-            if (j == p.n_blk - 1) tcgen05_commit(&o_full[t]);
+            if (!more) tcgen05_commit(&o_full[t]);
+            if (more) {
+              if (t == 0) { mbar_wait(&kv_full[sk], phk); tcgen05_fence_after(); }
+              issue_qk(t, k_addr);
+            }
           }
-          tcgen05_commit(&kv_empty[st]);
-          if (++st == ATL_NST) { st = 0; st_ph ^= 1; }
+          tcgen05_commit(&kv_empty[sv]);
+          if (more) tcgen05_commit(&kv_empty[sk]);
         }
         tcgen05_commit(&q_empty[qb]);
         for (int t = 0; t < nq; ++t) ++n_used[t];
@@ -171,11 +191,17 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     }
   } else if (warp_idx >= 4) {
     // ===================== softmax + output =====================
-    const int q = warp_idx & 3;
-    const int t = (warp_idx - 4) >> 2;
+    const int q = warp_idx & 3;              // TMEM lane quarter (hardware rule: warp % 4)
+    const int t = ((warp_idx - 4) >> 2) & 1; // query tile
+    const int hf = (warp_idx - 4) >> 3;      // column half: score chunks [3 hf, 3 hf + 3), O columns [32 hf, 32 hf + 32)
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+    float* my_x = xch + ((t * 128 + q * 32 + lane) * 2 + hf);
+    const float* peer_x = xch + ((t * 128 + q * 32 + lane) * 2 + (hf ^ 1));
+    const int pair_bar = 1 + t * 4 + q;      // named barrier of the two warps that share these rows
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
     uint32_t n_sfull = 0, n_ofull = 0, n_pv = 0;  // n_pv: P V blocks issued for this tile so far (phases of pv_done)
     constexpr int PT = FMT == 0 ? 1 : 2;
+    constexpr int CH = ATL_KB / 64;          // 32-column chunks per half block
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
       const int ue = p.reverse ? num_units - 1 - unit : unit;
       const int qp = ue % p.n_qp, bh = ue / p.n_qp;
@@ -183,94 +209,83 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
       const int nq = (S - qp * 256 > 128) ? 2 : 1;
       if (t >= nq) continue;
       const int row = qp * 256 + t * 128 + q * 32 + lane;
-      float ms = -INFINITY;  // reference maximum, already multiplied by scale_log2
+      float ms = -INFINITY;  // reference maximum (scaled by scale_log2), identical in both warps of the row
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
-      float2 mo2 = make_float2(0.f, 0.f);
-      float2 l2 = make_float2(0.f, 0.f);
-      uint32_t r[32], rn[32];
+      float2 l2 = make_float2(0.f, 0.f);   // this half's share of the row sum
+      uint32_t r[32];
       for (int j = 0; j < p.n_blk; ++j) {
         const int kvalid = min(ATL_KB, S - j * ATL_KB);   // valid keys in this block (only the last block is partial)
         const int n_live = (kvalid + 31) / 32, n_full = kvalid / 32;
         mbar_wait(&s_full[t], n_sfull & 1);
         ++n_sfull;
         tcgen05_fence_after();
-        auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
-          // chunk maximum; raise the reference only when it is exceeded by more than 8 (log2 domain)
-          float cm = -INFINITY;
+        // ---- pass 1: maximum of this half's columns, agreed with the other half through shared memory ----
+        float cm = -INFINITY;
+        for (int cc = 0; cc < CH; ++cc) {
+          const int c = hf * CH + cc;
+          if (c >= n_live) break;
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_ld_wait();
           if (c < n_full) {
 #pragma unroll
-            for (int jj = 0; jj < 32; jj += 2) cm = fmax3(cm, __uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1]));
+            for (int jj = 0; jj < 32; jj += 2) cm = fmax3(cm, __uint_as_float(r[jj]), __uint_as_float(r[jj + 1]));
           } else {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) cm = (c * 32 + jj < kvalid) ? fmaxf(cm, __uint_as_float(sv[jj])) : cm;
-          }
-          const float cs = cm * p.scale_log2;
-          const bool raise = cs > ms + 8.0f;
-          if (__any_sync(0xffffffffu, raise)) {
-            // rare: rescale what this row has accumulated under the old reference (lanes that do not raise use factor 1)
-            const float f = raise ? ex2_approx(ms - cs) : 1.0f;
-            l2.x *= f;
-            l2.y *= f;
-            for (int cc = 0; cc < c; ++cc) {  // P chunks of this block already written
-              uint32_t pk[16];
-              tmem_ld_32x32b_x16(taddr + cc * 16, pk);
-              tmem_ld_wait();
-#pragma unroll
-              for (int jj = 0; jj < 16; ++jj) {
-                float2 v;
-                if (PT == 1) v = __half22float2(*reinterpret_cast<const __half2*>(&pk[jj]));
-                else v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[jj]));
-                pk[jj] = pack2(v.x * f, v.y * f, PT);
-              }
-              tmem_st_32x32b_x16(taddr + cc * 16, pk);
-            }
-            if (j > 0) {  // O accumulated over the previous blocks: wait for the last P V, scale in place
-              mbar_wait(&pv_done[t], (n_pv - 1) & 1);
-              tcgen05_fence_after();
-#pragma unroll
-              for (int oc = 0; oc < 4; ++oc) {
-                uint32_t ov[16];
-                tmem_ld_32x32b_x16(taddr + 192 + oc * 16, ov);
-                tmem_ld_wait();
-#pragma unroll
-                for (int jj = 0; jj < 16; ++jj) ov[jj] = __float_as_uint(__uint_as_float(ov[jj]) * f);
-                tmem_st_32x32b_x16(taddr + 192 + oc * 16, ov);
-              }
-            }
-            tmem_st_wait();
-            if (raise) ms = cs;
-            mo2 = make_float2(-ms, -ms);
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int jj = 0; jj < 32; jj += 2) {
-            const float2 a = ffma2(make_float2(__uint_as_float(sv[jj]), __uint_as_float(sv[jj + 1])), sc2, mo2);
-            float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-            if (c >= n_full) {
-              e.x = (c * 32 + jj < kvalid) ? e.x : 0.f;
-              e.y = (c * 32 + jj + 1 < kvalid) ? e.y : 0.f;
-            }
-            l2 = fadd2(l2, e);
-            pk[jj >> 1] = pack2(e.x, e.y, PT);
-          }
-          tmem_st_32x32b_x16(taddr + c * 16, pk);
-        };
-        tmem_ld_32x32b_x32(taddr, r);
-        for (int c = 0; c < n_live; c += 2) {
-          tmem_ld_wait();
-          if (c + 1 < n_live) tmem_ld_32x32b_x32(taddr + (c + 1) * 32, rn);
-          softmax_chunk(r, c);
-          if (c + 1 < n_live) {
-            tmem_ld_wait();
-            if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
-            softmax_chunk(rn, c + 1);
+            for (int jj = 0; jj < 32; ++jj) cm = (c * 32 + jj < kvalid) ? fmaxf(cm, __uint_as_float(r[jj])) : cm;
           }
         }
-        for (int c = n_live; c < ATL_KB / 32; ++c) {  // keys beyond S: P = 0
-          uint32_t pk[16];
+        *my_x = cm;
+        pair_sync();
+        const float bs = fmaxf(cm, *peer_x) * p.scale_log2;  // block maximum of the whole row (chunk 0 is always live: finite)
+        pair_sync();                                          // both have read before either overwrites its slot again
+        const bool raise = bs > ms + 8.0f;                    // the same decision in both warps of the row
+        if (__any_sync(0xffffffffu, raise)) {
+          // rare after the first block: rescale what the row has accumulated under the old reference (factor 1 for rows that keep it)
+          const float f = raise ? ex2_approx(ms - bs) : 1.0f;
+          l2.x *= f;
+          l2.y *= f;
+          if (j > 0) {  // this half's 32 columns of O: wait for the last P V, scale in place
+            mbar_wait(&pv_done[t], (n_pv - 1) & 1);
+            tcgen05_fence_after();
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) pk[jj] = 0u;
-          tmem_st_32x32b_x16(taddr + c * 16, pk);
+            for (int oc = 0; oc < 2; ++oc) {
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(taddr + 192 + hf * 32 + oc * 16, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int jj = 0; jj < 16; ++jj) ov[jj] = __float_as_uint(__uint_as_float(ov[jj]) * f);
+              tmem_st_32x32b_x16(taddr + 192 + hf * 32 + oc * 16, ov);
+            }
+            tmem_st_wait();
+          }
+          if (raise) ms = bs;
+        }
+        const float2 mo2 = make_float2(-ms, -ms);
+        // ---- pass 2: P = exp2(S * scale - ms) over this half's chunks ----
+        for (int cc = 0; cc < CH; ++cc) {
+          const int c = hf * CH + cc;
+          uint32_t pk[16];
+          if (c < n_live) {
+            tmem_ld_32x32b_x32(taddr + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int jj = 0; jj < 32; jj += 2) {
+              const float2 a = ffma2(make_float2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), sc2, mo2);
+              float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+              if (c >= n_full) {
+                e.x = (c * 32 + jj < kvalid) ? e.x : 0.f;
+                e.y = (c * 32 + jj + 1 < kvalid) ? e.y : 0.f;
+              }
+              l2 = fadd2(l2, e);
+              pk[jj >> 1] = pack2(e.x, e.y, PT);
+            }
+          } else {  // keys beyond S: P = 0
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) pk[jj] = 0u;
+          }
+          // P of half hf lives at columns [96 hf + 16 cc, +16): inside this half's OWN score columns and always behind its read position
+          // (chunk 3 hf + cc has just been read), so the two halves never touch each other's unread scores.
+          tmem_st_32x32b_x16(taddr + hf * 96 + cc * 16, pk);
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -278,20 +293,22 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         if (lane == 0) mbar_arrive(&p_ready[t]);
         ++n_pv;
       }
-      // ---- output ----
-      const float inv = 1.0f / (l2.x + l2.y);
+      // ---- output: this half's 32 columns of O / l ----
+      *my_x = l2.x + l2.y;
+      pair_sync();
+      const float inv = 1.0f / (l2.x + l2.y + *peer_x);
+      pair_sync();
       mbar_wait(&o_full[t], n_ofull & 1);
       ++n_ofull;
       tcgen05_fence_after();
-      uint32_t o0[32], o1[32];
-      tmem_ld_32x32b_x32(taddr + 192, o0);
-      tmem_ld_32x32b_x32(taddr + 224, o1);
+      uint32_t o0[32];
+      tmem_ld_32x32b_x32(taddr + 192 + hf * 32, o0);
       tmem_ld_wait();
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
       if (row < S) {
-        const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64;
+        const size_t off = (static_cast<size_t>(b) * S + row) * p.D + h * 64 + hf * 32;
         if constexpr (sizeof(OutT) == 2) {
           uint4* dst = reinterpret_cast<uint4*>(static_cast<uint16_t*>(p.out) + off);
           constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
@@ -301,12 +318,6 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                                  pack2(__uint_as_float(o0[8 * jj + 2]) * inv, __uint_as_float(o0[8 * jj + 3]) * inv, ot),
                                  pack2(__uint_as_float(o0[8 * jj + 4]) * inv, __uint_as_float(o0[8 * jj + 5]) * inv, ot),
                                  pack2(__uint_as_float(o0[8 * jj + 6]) * inv, __uint_as_float(o0[8 * jj + 7]) * inv, ot));
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj)
-            dst[4 + jj] = make_uint4(pack2(__uint_as_float(o1[8 * jj]) * inv, __uint_as_float(o1[8 * jj + 1]) * inv, ot),
-                                     pack2(__uint_as_float(o1[8 * jj + 2]) * inv, __uint_as_float(o1[8 * jj + 3]) * inv, ot),
-                                     pack2(__uint_as_float(o1[8 * jj + 4]) * inv, __uint_as_float(o1[8 * jj + 5]) * inv, ot),
-                                     pack2(__uint_as_float(o1[8 * jj + 6]) * inv, __uint_as_float(o1[8 * jj + 7]) * inv, ot));
         } else {
           float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out) + off);
           constexpr bool RT = std::is_same<OutT, tf32_t>::value;
@@ -316,13 +327,6 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
                                    __uint_as_float(o0[4 * jj + 3]) * inv);
             if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
             dst[jj] = v;
-          }
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float4 v = make_float4(__uint_as_float(o1[4 * jj]) * inv, __uint_as_float(o1[4 * jj + 1]) * inv, __uint_as_float(o1[4 * jj + 2]) * inv,
-                                   __uint_as_float(o1[4 * jj + 3]) * inv);
-            if (RT) v = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
-            dst[8 + jj] = v;
           }
         }
       }

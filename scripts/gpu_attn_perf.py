@@ -12,7 +12,10 @@ from gpu_util import F16, check, ptr, stream
 from jimm_b200 import _lib
 
 lib = _lib.load()
-for (B, S, H, causal) in ((256, 197, 12, 0), (256, 256, 12, 0), (256, 50, 12, 0), (256, 77, 8, 1), (128, 576, 16, 0), (32, 1024, 16, 0)):
+CASES = ((256, 197, 12, 0), (256, 256, 12, 0), (256, 50, 12, 0), (256, 77, 8, 1), (128, 576, 16, 0), (32, 1024, 16, 0))
+if os.environ.get("ONLY_S"):
+    CASES = tuple(c for c in CASES if c[1] == int(os.environ["ONLY_S"]))
+for (B, S, H, causal) in CASES:
     qkv = torch.randn(B * S, 3 * H * 64, device="cuda").half()
     out = torch.empty(B * S, H * 64, dtype=torch.float16, device="cuda")
     for _ in range(3):
