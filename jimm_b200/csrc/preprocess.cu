@@ -105,7 +105,7 @@ struct KernelArgs {
   const int *hfirst, *hcount, *hk;     // horizontal tables, already offset to the first cropped column
   const int *vfirst, *vcount, *vk;     // vertical tables, already offset to the first cropped row
   int H, W, oh, ow, hks, hstride, vks;  // hks / vks: taps rounded up to a multiple of 4; hstride: row stride of hk
-  int TY, G, tile_rows;                // output rows per CTA, input rows per staging group, capacity of the 8-bit tile
+  int TY;                              // output rows per CTA
   int rowb;                            // bytes per tile row (ow*3 rounded up to 4)
   int stage_bytes;                     // one warp's row buffer (W*3 + 32, rounded to 16)
   int vec_ok;                          // img is 16-byte aligned
@@ -264,7 +264,7 @@ struct DevTable {
 struct SizePlan {
   int rh = 0, rw = 0, top = 0, left = 0, oh = 0, ow = 0;
   DevTable h, v;
-  int TY = 0, G = 0, tile_rows = 0, rowb = 0, stage_bytes = 0;
+  int TY = 0, tile_rows = 0, rowb = 0, stage_bytes = 0;
   size_t smem = 0;
 };
 
@@ -339,7 +339,6 @@ int get_plan(jimm_preproc* p, int H, int W, SizePlan** out) {
   if (row_bytes + 3 * th.kpad + 48 > 64 * 1024) { set_last_error("image width %d too large for the staging buffer", W); return JIMM_EINVAL; }
   s.rowb = (s.ow * 3 + 3) / 4 * 4;
   const size_t tables = (static_cast<size_t>(s.ow) * s.h.stride + s.ow) * sizeof(int) + 16;
-  s.G = 1;
   s.stage_bytes = static_cast<int>((row_bytes + 15 + 3 * th.kpad + 8 + 15) / 16 * 16);  // alignment shift + zero-weight taps past the row + word read-ahead
   // Largest tile of output rows (<= 32) that fits three CTAs per SM; when that leaves fewer than 16 rows (wide inputs, large
   // outputs) the halo rows recomputed per tile dominate, so trade occupancy for a taller tile: two CTAs, then one.
@@ -436,7 +435,7 @@ int jimm_preproc_run(jimm_preproc_t* p, const uint8_t* img, int B, int H, int W,
   a.vcount = s->v.count + s->top;
   a.vk = s->v.kk + static_cast<size_t>(s->top) * s->v.ksize;
   a.H = H; a.W = W; a.oh = s->oh; a.ow = s->ow; a.hks = s->h.ksize; a.hstride = s->h.stride; a.vks = s->v.ksize;
-  a.TY = s->TY; a.G = s->G; a.tile_rows = s->tile_rows; a.rowb = s->rowb; a.stage_bytes = s->stage_bytes;
+  a.TY = s->TY; a.rowb = s->rowb; a.stage_bytes = s->stage_bytes;
   a.vec_ok = (reinterpret_cast<uintptr_t>(img) & 15) == 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // the grid's y dimension is limited to 65535 images per launch
