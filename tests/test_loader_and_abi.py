@@ -171,3 +171,39 @@ def test_random_init_distributions():
     m2 = VisionTransformer(num_classes=12, img_size=32, patch_size=8, num_layers=1, num_heads=2, mlp_dim=256, hidden_size=128, rngs=Rngs(0))
     assert torch.equal(p["classifier.kernel"], m2.flat_params()["classifier.kernel"])
     assert m.eval() is m and m.training is False and m.train().training is True
+
+
+def test_front_end_and_epilogue_fail_loudly_without_gpu():
+    """No CPU fallback for the image front-end / zero-shot epilogue either; argument errors keep the HF processors' types."""
+    import numpy as np
+    import torch
+
+    from jimm_b200 import _lib
+    from jimm_b200.postprocess import zero_shot
+    from jimm_b200.preprocess import ImagePreprocessor, _size_fields
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    with pytest.raises(_lib.JimmError):
+        ImagePreprocessor.vit(224)
+    with pytest.raises(_lib.JimmError):
+        zero_shot(torch.zeros(2, 3))
+    with pytest.raises(ValueError):
+        ImagePreprocessor(size={"height": 8, "width": 8}, resample=1)
+    with pytest.raises(ValueError):
+        ImagePreprocessor(size={"height": 8, "width": 8}, image_std=(0.5, 0.0, 0.5))
+    with pytest.raises(ValueError):
+        ImagePreprocessor(size={"longest_edge": 8})
+    assert _size_fields(224) == {"shortest_edge": 224}
+    assert _size_fields({"height": 3, "width": 5}) == {"height": 3, "width": 5}
+    assert _size_fields((7, 9)) == {"height": 7, "width": 9}
+
+
+def test_pending_result_of_a_finished_call():
+    import torch
+
+    from jimm_b200._runtime import PendingResult
+
+    t = torch.arange(4.0)
+    p = PendingResult(t, None)
+    assert p.done() and p.result() is t
