@@ -1,14 +1,16 @@
 #!/usr/bin/env python
 """bench.py -- images/sec of the ViT forward hot path on B200 (BASELINE.json metric), one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vit_b16|vit_l16_map|clip_b32|siglip_b16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload vit_b16|vit_l16_map|clip_b32|siglip_b16|siglip2_l16_512]
 
 A "step" is one forward pass of the hot path over one synthetic batch.  The default workload is BASELINE.json configs[1]:
 ViT-B/16 @224, batch 256 per GPU, fp16 tensor-core operands (fp32 accumulate / residual / LN / softmax), random-init weights.
   value  : whole-job images/sec with the inputs already resident in HBM (CUDA events, barrier + synchronize both sides,
            max over ranks).  Weak scaling: every rank runs its own 256-image batch; no data-path collective for ViT.
   e2e    : the same metric through the public Python API with HOST (pinned) inputs: H2D copy + forward + D2H of the logits
-           inside the timed region (jimm_vit_forward_host).
+           inside the timed region (jimm_vit_forward_host), with a synchronisation every step.  `pipelined_depth2_value` is the
+           same loop through `forward_async` with two calls in flight (every step still copies its inputs in and its result out);
+           it is an extra, not the headline.
   roofline: the dominant kernel (tcgen05 GEMM) timed live with CUDA events around every launch of the timed steps.
   cpu_baseline: the CPU oracle (torch fp32, jimm semantics -- the stand-in for the reference's JAX-CPU path, which cannot
            be installed here) on a bounded sample, rank 0 / N=1 only.
