@@ -405,3 +405,49 @@ def test_async_host_pipeline(vitb16):
         assert not o.is_cuda and torch.equal(o, sync[k])
     assert torch.equal(dev_out.cpu(), sync[0])
     assert torch.equal(sync[1], torch.flip(sync[0], dims=[0]))
+
+
+def test_config3_full_depth_vit_l16_384_map_bf16():
+    """BASELINE config 3 at its real depth (24 layers, 316 M parameters), two images: the long-sequence attention, the MAP head and 96
+    chained bf16 GEMMs against the same-rounding oracle and the fp32 oracle."""
+    from jimm_b200.common.vit import VisionTransformerBase
+
+    t = O.TowerCfg(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=24, num_heads=16, mlp_dim=4096,
+                   pooling_type="MAP", layernorm_epsilon=1e-6)
+    p = O.random_tower_params(t, seed=15)
+    img = O.synthetic_images(2, 384, seed=77)
+    with torch.no_grad():
+        ref = O.vision_tower(p, "", img, t)
+        ref_same = O.vision_tower(p, "", img, t, O.Semantics(operand_round="bf16"))
+    m = _set(VisionTransformerBase(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=24, num_heads=16, mlp_dim=4096,
+                                   pooling_type="MAP", layernorm_epsilon=1e-6, dtype=torch.bfloat16), p)
+    out = m(img.cuda())
+    assert out.shape == (2, 1024) and torch.isfinite(out).all()
+    assert rel(out, ref_same) < 8e-3 and rel(out, ref) < 1.5e-2, (rel(out, ref_same), rel(out, ref))
+    m16 = _set(VisionTransformerBase(img_size=384, patch_size=16, in_channels=3, hidden_size=1024, num_layers=24, num_heads=16, mlp_dim=4096,
+                                     pooling_type="MAP", layernorm_epsilon=1e-6, dtype=torch.float16), p)
+    r16 = rel(m16(img.cuda()), ref)
+    assert r16 < 2e-3, r16  # fp16 operands over 24 layers; config 2's 1e-3 bar is for the 12-layer ViT-B
+
+
+def test_config5_full_depth_siglip2_l16_512_bf16():
+    """BASELINE config 5 towers at their real depth (vision 24 x 1024 @512 -> S = 1024, text 24 x 1024, T = 64; reduced vocabulary), one image
+    and two texts, bf16 against the same-rounding oracle."""
+    from jimm_b200.models import SigLIP
+
+    cfg = O.DualCfg(512, 24, 1024, 16, 64, 4096, 1024, 16, 24)
+    p = O.random_dual_params(cfg, "siglip", seed=19)
+    img, txt = O.synthetic_images(1, 512, seed=5), O.synthetic_tokens(2, 64, 4096, "siglip", seed=6)
+    sem = O.Semantics(operand_round="bf16")
+    with torch.no_grad():
+        ref_i = O.siglip_encode_image(p, cfg, img)
+        ref_i_same = O.siglip_encode_image(p, cfg, img, sem) if "sem" in O.siglip_encode_image.__code__.co_varnames else None
+        ref = O.siglip_forward(p, cfg, img, txt)
+    m = _set(SigLIP(512, 24, 1024, 16, 64, 4096, 1024, 16, 24, dtype=torch.bfloat16), p)
+    emb = m.encode_image(img.cuda())
+    assert emb.shape == (1, 1024) and torch.isfinite(emb).all()
+    if ref_i_same is not None:
+        assert rel(emb, ref_i_same) < 8e-3, rel(emb, ref_i_same)
+    assert rel(emb, ref_i) < 2e-2, rel(emb, ref_i)
+    out = m(img.cuda(), txt.cuda())
+    assert out.shape == (1, 2) and rel(out, ref) < 2e-2, rel(out, ref)
