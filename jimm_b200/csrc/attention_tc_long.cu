@@ -122,7 +122,10 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
+      // The whole warp runs this control flow (waits, counters, addresses stay warp-uniform: the compiler can keep the MMA operands in
+      // uniform registers); only the elected lane issues the tcgen05 instructions.
+      const bool leader = lane == 0;
       const uint32_t idesc_qk = make_idesc(FMT, 128, ATL_KB, 0);
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);
       int st = 0;
@@ -142,16 +145,16 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
           // them, and the tensor pipe executes in issue order.
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
+            if (leader) umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
                        k > 0 ? 1u : 0u);
-          tcgen05_commit(&s_full[t]);
+          if (leader) tcgen05_commit(&s_full[t]);
         };
         auto next_stage = [&]() { if (++st == ATL_NST) { st = 0; st_ph ^= 1; } };
         // prologue: scores of block 0 for both tiles
         mbar_wait(&kv_full[st], st_ph);
         tcgen05_fence_after();
         for (int t = 0; t < nq; ++t) issue_qk(t, smem_u32(smem_kv + st * ATL_KV_BYTES));
-        tcgen05_commit(&kv_empty[st]);
+        if (leader) tcgen05_commit(&kv_empty[st]);
         next_stage();
         for (int j = 0; j < p.n_blk; ++j) {
           // Per tile: O_t += P_t V_j as soon as ITS softmax is done, immediately followed by ITS next scores S_t = Q_t K_{j+1}^T -- the
@@ -173,19 +176,19 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             tcgen05_fence_after();
 #pragma unroll
             for (int kk = 0; kk < ATL_KB / 16; ++kk)
-              umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + (kk < ATL_KB / 32 ? kk * 8 : 96 + (kk - ATL_KB / 32) * 8),
+              if (leader) umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + (kk < ATL_KB / 32 ? kk * 8 : 96 + (kk - ATL_KB / 32) * 8),
                           make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0 ? 1u : 0u);  // P: keys 0-95 at columns 0-47, keys 96-191 at 96-143
-            tcgen05_commit(&pv_done[t]);
-            if (!more) tcgen05_commit(&o_full[t]);
+            if (leader) tcgen05_commit(&pv_done[t]);
+            if (!more && leader) tcgen05_commit(&o_full[t]);
             if (more) {
               if (t == 0) { mbar_wait(&kv_full[sk], phk); tcgen05_fence_after(); }
               issue_qk(t, k_addr);
             }
           }
-          tcgen05_commit(&kv_empty[sv]);
-          if (more) tcgen05_commit(&kv_empty[sk]);
+          if (leader) tcgen05_commit(&kv_empty[sv]);
+          if (more && leader) tcgen05_commit(&kv_empty[sk]);
         }
-        tcgen05_commit(&q_empty[qb]);
+        if (leader) tcgen05_commit(&q_empty[qb]);
         for (int t = 0; t < nq; ++t) ++n_used[t];
       }
     }
