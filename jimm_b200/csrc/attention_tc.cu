@@ -110,7 +110,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    {
+      // The whole warp runs this control flow (waits, counters and descriptors stay warp-uniform, i.e. in uniform registers); only the
+      // elected lane issues the tcgen05 instructions.  With 16 small MMAs per item the issue cost matters (long kernel: -4 %).
+      const bool leader = lane == 0;
       const uint32_t idesc_qk = make_idesc(FMT, 128, static_cast<uint32_t>(p.Nk), 0);
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
       int it = 0;
@@ -118,27 +121,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const int buf = it & 1;
         const uint32_t ph = (it >> 1) & 1, sp = it & 1;
         const uint32_t q_addr = smem_u32(smem + buf * ATC_BUF_BYTES);
-        const uint32_t k_addr = q_addr + ATC_TILE_BYTES, v_addr = q_addr + 2 * ATC_TILE_BYTES;
+        // descriptors advance by (bytes >> 4) in their address field: 32 B per 16-element K step, 2048 B per 16 keys of V
+        const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + ATC_TILE_BYTES),
+                       vdesc = make_umma_desc_sw128(q_addr + 2 * ATC_TILE_BYTES);
         mbar_wait(&kv_full[buf], ph);
         tcgen05_fence_after();
         for (int t = 0; t < p.nq; ++t) {
           mbar_wait(&slot_free[t], sp ^ 1);  // the previous item's O of this tile has been read out
           tcgen05_fence_after();
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32),
-                       idesc_qk, k > 0 ? 1u : 0u);
-          tcgen05_commit(&s_full[t]);
+            for (int k = 0; k < 4; ++k)
+              umma_ss<0>(tmem_base + t * 256, qdesc + static_cast<uint64_t>(t * (16384 >> 4) + k * 2), kdesc + static_cast<uint64_t>(k * 2), idesc_qk,
+                         k > 0 ? 1u : 0u);
+            tcgen05_commit(&s_full[t]);
+          }
         }
         for (int t = 0; t < p.nq; ++t) {
           mbar_wait(&p_ready[t], sp);
           tcgen05_fence_after();
-          for (int kk = 0; kk < p.Nk / 16; ++kk)
-            umma_ts_f16(tmem_base + t * 256 + 128, tmem_base + t * 256 + kk * 8, make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv,
-                        kk > 0 ? 1u : 0u);
-          tcgen05_commit(&o_full[t]);
+          if (leader) {
+            for (int kk = 0; kk < p.Nk / 16; ++kk)
+              umma_ts_f16(tmem_base + t * 256 + 128, tmem_base + t * 256 + kk * 8, vdesc + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
+                          kk > 0 ? 1u : 0u);
+            tcgen05_commit(&o_full[t]);
+          }
         }
-        tcgen05_commit(&kv_empty[buf]);  // every MMA reading this item's smem has retired
+        if (leader) tcgen05_commit(&kv_empty[buf]);  // every MMA reading this item's smem has retired
       }
     }
   } else if (warp_idx >= 4) {

@@ -140,14 +140,18 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
         const uint32_t q_addr = smem_u32(smem_q + qb * ATL_Q_BYTES);
         mbar_wait(&q_full[qb], (ui >> 1) & 1);
         tcgen05_fence_after();
+        const uint64_t qdesc = make_umma_desc_sw128(q_addr);  // descriptors advance by (bytes >> 4) in their address field
         auto issue_qk = [&](int t, uint32_t k_addr) {
           // S_t = Q_t K^T.  The S / P columns of tile t are free: its previous P V was issued after the softmax warps had finished with
           // them, and the tensor pipe executes in issue order.
+          if (leader) {
+            const uint64_t kdesc = make_umma_desc_sw128(k_addr);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (leader) umma_ss<0>(tmem_base + t * 256, make_umma_desc_sw128(q_addr + t * 16384 + k * 32), make_umma_desc_sw128(k_addr + k * 32), idesc_qk,
-                       k > 0 ? 1u : 0u);
-          if (leader) tcgen05_commit(&s_full[t]);
+            for (int k = 0; k < 4; ++k)
+              umma_ss<0>(tmem_base + t * 256, qdesc + static_cast<uint64_t>(t * (16384 >> 4) + k * 2), kdesc + static_cast<uint64_t>(k * 2), idesc_qk,
+                         k > 0 ? 1u : 0u);
+            tcgen05_commit(&s_full[t]);
+          }
         };
         auto next_stage = [&]() { if (++st == ATL_NST) { st = 0; st_ph ^= 1; } };
         // prologue: scores of block 0 for both tiles
@@ -174,10 +178,13 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
             if (j == 0 && n_used[t] > 0) mbar_wait(&o_free[t], (n_used[t] - 1) & 1);  // previous unit's O of this tile was read out
             if (t == 0) mbar_wait(&kv_full[sv], phv);
             tcgen05_fence_after();
+            if (leader) {
+              const uint64_t vdesc = make_umma_desc_sw128(v_addr);
 #pragma unroll
-            for (int kk = 0; kk < ATL_KB / 16; ++kk)
-              if (leader) umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + (kk < ATL_KB / 32 ? kk * 8 : 96 + (kk - ATL_KB / 32) * 8),
-                          make_umma_desc_sw128(v_addr + kk * 2048), idesc_pv, (j | kk) != 0 ? 1u : 0u);  // P: keys 0-95 at columns 0-47, keys 96-191 at 96-143
+              for (int kk = 0; kk < ATL_KB / 16; ++kk)
+                umma_ts_f16(tmem_base + t * 256 + 192, tmem_base + t * 256 + (kk < ATL_KB / 32 ? kk * 8 : 96 + (kk - ATL_KB / 32) * 8),
+                            vdesc + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv, (j | kk) != 0 ? 1u : 0u);  // P: keys 0-95 at columns 0-47, 96-191 at 96-143
+            }
             if (leader) tcgen05_commit(&pv_done[t]);
             if (!more && leader) tcgen05_commit(&o_full[t]);
             if (more) {
