@@ -396,7 +396,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer (pair mode: the leader CTA only) =====================
-    if (lane == 0 && cta_rank == 0) {
+    // The whole warp runs the control flow (waits, counters and descriptors stay warp-uniform); only the elected lane issues.
+    if (cta_rank == 0) {
+      const bool leader = lane == 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -408,21 +410,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_BYTES);
+          if (leader) {
+            const uint64_t adesc = make_umma_desc_sw128(smem_u32(smem_a + stage * A_STAGE_BYTES));
+            const uint64_t bdesc = make_umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adesc = make_umma_desc_sw128(a_addr + k * 32);
-            const uint64_t bdesc = make_umma_desc_sw128(b_addr + k * 32);
-            if constexpr (PAIR) umma_ss_pair<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
-            else umma_ss<Traits<T>::KIND>(tmem_d, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
-          }
-          if constexpr (PAIR) {
-            tcgen05_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs once the MMAs above retire
-            if (kb == num_kb - 1) tcgen05_commit_pair(&tmem_full_bar[acc]);
-          } else {
-            tcgen05_commit(&empty_bar[stage]);
-            if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc]);
+            for (int k = 0; k < BK / UK; ++k) {  // descriptors advance by 32 bytes (>> 4) per UMMA K step
+              if constexpr (PAIR) umma_ss_pair<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (PAIR) {
+              tcgen05_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs once the MMAs above retire
+              if (kb == num_kb - 1) tcgen05_commit_pair(&tmem_full_bar[acc]);
+            } else {
+              tcgen05_commit(&empty_bar[stage]);
+              if (kb == num_kb - 1) tcgen05_commit(&tmem_full_bar[acc]);
+            }
           }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
