@@ -62,8 +62,21 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.rows = []
+        self.rows = []   # (arrival time, csv line)
         self.proc = None
+        self.t0 = self.t1 = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def in_window(self) -> int:
+        """Samples that arrived while the timed region ran (a sample describes the ~100 ms before it arrives)."""
+        if self.t0 is None or self.t1 is None:
+            return len(self.rows)
+        return sum(1 for t, _ in self.rows if self.t0 <= t <= self.t1 + 0.12)
 
     def start(self):
         try:
@@ -76,7 +89,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
 
     def stop(self):
         if self.proc is None:
@@ -88,7 +101,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows
+        if self.t0 is not None and self.t1 is not None:
+            lo = self.t0 if self.in_window() else self.t1  # no sample inside the region: the post-region load at the same clocks (see caller)
+            rows = [(t, r) for t, r in self.rows if t >= lo] or self.rows[-3:]  # multi-GPU runs cannot extend the load: warm-up samples
+        for _, r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -274,20 +291,31 @@ def run_ours(args):
         barrier()
         return jd.max_over_ranks(e0.elapsed_time(e1)), out
 
-    # ---- warm-up (also builds the native handle) ----
+    # ---- warm-up (also builds the native handle); the clock sampler is started first so that nvidia-smi is already streaming
+    #      when the timed region begins (its start-up can take longer than a short timed region) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_dev()
     torch.cuda.synchronize(dev)
     native = model.native(B)
 
     # ---- value: device-resident inputs ----
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = lib.jimm_launch_count()
+    sampler.mark_begin()
     ms_total, out = timed(step_dev, args.steps)
+    sampler.mark_end()
     launches = lib.jimm_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        if sampler.proc is not None and sampler.in_window() == 0 and world == 1:
+            # the region was shorter than the sampling period: keep the same load running (untimed) until a sample lands
+            t_wait = time.time()
+            while len([1 for t, _ in sampler.rows if t >= sampler.t1]) < 2 and time.time() - t_wait < 3.0:
+                step_dev()
+                torch.cuda.synchronize(dev)
+        clocks = sampler.stop()
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
 
