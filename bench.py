@@ -78,6 +78,14 @@ class ClockSampler:
             return len(self.rows)
         return sum(1 for t, _ in self.rows if self.t0 <= t <= self.t1 + 0.12)
 
+    def selected_rows(self):
+        """Samples of the timed region; if the region was too short for one, those of the post-region load the caller kept running
+        (single GPU) or, failing that, the last warm-up samples (multi-GPU runs cannot extend the load unilaterally)."""
+        if self.t0 is None or self.t1 is None:
+            return list(self.rows)
+        lo = self.t0 if self.in_window() else self.t1
+        return [(t, r) for t, r in self.rows if t >= lo] or self.rows[-3:]
+
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -101,11 +109,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        rows = self.rows
-        if self.t0 is not None and self.t1 is not None:
-            lo = self.t0 if self.in_window() else self.t1  # no sample inside the region: the post-region load at the same clocks (see caller)
-            rows = [(t, r) for t, r in self.rows if t >= lo] or self.rows[-3:]  # multi-GPU runs cannot extend the load: warm-up samples
-        for _, r in rows:
+        for _, r in self.selected_rows():
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue

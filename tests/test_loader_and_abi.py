@@ -207,3 +207,21 @@ def test_pending_result_of_a_finished_call():
     t = torch.arange(4.0)
     p = PendingResult(t, None)
     assert p.done() and p.result() is t
+
+
+def test_bench_clock_sampler_window():
+    """bench.py keeps the nvidia-smi samples of the timed region, else the post-region load, else the last warm-up samples."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.rows = [(10.0, "w1"), (10.1, "w2"), (10.2, "w3"), (10.3, "w4")]
+    assert [r for _, r in s.selected_rows()] == ["w1", "w2", "w3", "w4"]  # no marks: everything
+    s.t0, s.t1 = 10.15, 10.25
+    assert [r for _, r in s.selected_rows()] == ["w3", "w4"]  # inside the region (+ one trailing period)
+    s.t0, s.t1 = 10.31, 10.32  # region shorter than a sampling period, nothing after it: fall back to the last warm-up samples
+    assert [r for _, r in s.selected_rows()] == ["w2", "w3", "w4"]
+    s.rows.append((10.5, "post"))  # the caller kept the load running until a sample landed
+    assert [r for _, r in s.selected_rows()] == ["post"]
