@@ -80,9 +80,29 @@ class Semantics:
     gelu: str = "tanh"  # nnx.gelu default approximate=True (common/transformer.py:90, common/vit.py:75)
     block_eps: Optional[float] = None  # None -> Transformer default 1e-6 (common/transformer.py:142)
     operand_round: Optional[str] = None  # None | "fp16" | "bf16" | "tf32"
+    # flax `dtype=` semantics ([flax-knowledge], flax 0.10.6 nnx/nn/linear.py, normalization.py, attention.py): with
+    # dtype=bf16 every layer promotes its inputs AND parameters to bf16 (promote_dtype) and returns a bf16 array, so the
+    # residual stream, every bias add, every activation and the softmax are rounded to bf16; only the LayerNorm statistics
+    # are computed in fp32.  That is the path examples/vit_inference.py:14-21 takes (from_pretrained(..., dtype=jnp.bfloat16),
+    # models/vit.py:181-182 also sets param_dtype=dtype).  act_round="bf16" (with operand_round="bf16") restates it: every
+    # op output below goes through _out().  The dot_general accumulates in fp32 and rounds once (XLA CPU), softmax is
+    # rounded after the normalisation only (XLA fuses the elementwise chain in fp32) -- both are statements about the
+    # absent third-party library, see the header.
+    act_round: Optional[str] = None  # None | "bf16" | "fp16"
 
 
 JIMM = Semantics()
+FLAX_BF16 = Semantics(operand_round="bf16", act_round="bf16")
+
+
+def _out(x: torch.Tensor, sem: "Semantics") -> torch.Tensor:
+    """Round a layer output to the flax compute dtype (identity in fp32 semantics)."""
+    return x if sem.act_round is None else round_operand(x, sem.act_round)
+
+
+def _prm(x: torch.Tensor, sem: "Semantics") -> torch.Tensor:
+    """A parameter as the layer sees it after promote_dtype (biases, LN scale/bias, cls, pos, scalars)."""
+    return x if sem.act_round is None else round_operand(x, sem.act_round)
 
 
 # --------------------------------------------------------------------------- #
@@ -90,16 +110,17 @@ JIMM = Semantics()
 # --------------------------------------------------------------------------- #
 def linear(x, kernel, bias=None, sem: Semantics = JIMM):
     """nnx.Linear: y = x @ kernel (+ bias); kernel is (in, out)."""
-    y = round_operand(x, sem.operand_round) @ round_operand(kernel, sem.operand_round)
-    return y if bias is None else y + bias
+    y = _out(round_operand(x, sem.operand_round) @ round_operand(kernel, sem.operand_round), sem)
+    return y if bias is None else _out(y + _prm(bias, sem), sem)
 
 
-def layer_norm(x, scale, bias, eps):
-    """nnx.LayerNorm with use_fast_variance=True: var = max(0, E[x^2] - E[x]^2)."""
+def layer_norm(x, scale, bias, eps, sem: "Semantics" = None):
+    """nnx.LayerNorm with use_fast_variance=True: var = max(0, E[x^2] - E[x]^2); statistics in fp32 whatever `dtype`."""
+    sem = sem or JIMM
     mean = x.mean(-1, keepdim=True)
     mean2 = (x * x).mean(-1, keepdim=True)
     var = torch.clamp(mean2 - mean * mean, min=0.0)
-    return (x - mean) * torch.rsqrt(var + eps) * scale + bias
+    return _out((x - mean) * torch.rsqrt(var + eps) * _prm(scale, sem) + _prm(bias, sem), sem)
 
 
 def gelu_tanh(x):
@@ -114,10 +135,10 @@ def quickgelu(x):
 
 def _act(x, use_quick_gelu: bool, sem: Semantics):
     if use_quick_gelu:
-        return quickgelu(x)
+        return _out(quickgelu(x), sem)
     if sem.gelu == "erf":
         return torch.nn.functional.gelu(x)
-    return gelu_tanh(x)
+    return _out(gelu_tanh(x), sem)
 
 
 def multi_head_attention(p: Params, prefix: str, xq, xkv, num_heads: int, mask=None, sem: Semantics = JIMM):
@@ -129,22 +150,23 @@ def multi_head_attention(p: Params, prefix: str, xq, xkv, num_heads: int, mask=N
     D, H, d = Wq.shape
     assert H == num_heads
     r = lambda t: round_operand(t, sem.operand_round)
-    q = r(xq) @ r(Wq.reshape(D, H * d)) + p[prefix + "query.bias"].reshape(H * d)
-    k = r(xkv) @ r(Wk.reshape(D, H * d)) + p[prefix + "key.bias"].reshape(H * d)
-    v = r(xkv) @ r(Wv.reshape(D, H * d)) + p[prefix + "value.bias"].reshape(H * d)
+    o_ = lambda t: _out(t, sem)
+    q = o_(o_(r(xq) @ r(Wq.reshape(D, H * d))) + _prm(p[prefix + "query.bias"].reshape(H * d), sem))
+    k = o_(o_(r(xkv) @ r(Wk.reshape(D, H * d))) + _prm(p[prefix + "key.bias"].reshape(H * d), sem))
+    v = o_(o_(r(xkv) @ r(Wv.reshape(D, H * d))) + _prm(p[prefix + "value.bias"].reshape(H * d), sem))
     B, Sq, _ = q.shape
     Sk = k.shape[1]
-    q = q.reshape(B, Sq, H, d).permute(0, 2, 1, 3) / math.sqrt(d)
+    q = o_(q.reshape(B, Sq, H, d).permute(0, 2, 1, 3) / math.sqrt(d))
     k = k.reshape(B, Sk, H, d).permute(0, 2, 1, 3)
     v = v.reshape(B, Sk, H, d).permute(0, 2, 1, 3)
-    w = r(q) @ r(k).transpose(-1, -2)  # [B,H,Sq,Sk]
+    w = o_(r(q) @ r(k).transpose(-1, -2))  # [B,H,Sq,Sk]
     if mask is not None:
         w = torch.where(mask != 0, w, torch.finfo(w.dtype).min)
-    w = torch.softmax(w, dim=-1)
-    o = r(w) @ r(v)  # [B,H,Sq,d]
+    w = o_(torch.softmax(w, dim=-1))
+    o = o_(r(w) @ r(v))  # [B,H,Sq,d]
     o = o.permute(0, 2, 1, 3).reshape(B, Sq, H * d)
     Wo = p[prefix + "out.kernel"].reshape(H * d, D)
-    return r(o) @ r(Wo) + p[prefix + "out.bias"]
+    return o_(o_(r(o) @ r(Wo)) + _prm(p[prefix + "out.bias"], sem))
 
 
 # --------------------------------------------------------------------------- #
@@ -155,13 +177,13 @@ def transformer_encoder(p: Params, prefix: str, x, num_heads, eps, use_quick_gel
     if mask is not None:
         s = min(x.shape[1], mask.shape[0])  # :125-129
         mask = mask[:s, :s]
-    h = layer_norm(x, p[prefix + "norm1.scale"], p[prefix + "norm1.bias"], eps)
-    x = x + multi_head_attention(p, prefix + "attn.", h, h, num_heads, mask, sem)  # :130
-    h = layer_norm(x, p[prefix + "norm2.scale"], p[prefix + "norm2.bias"], eps)
+    h = layer_norm(x, p[prefix + "norm1.scale"], p[prefix + "norm1.bias"], eps, sem)
+    x = _out(x + multi_head_attention(p, prefix + "attn.", h, h, num_heads, mask, sem), sem)  # :130
+    h = layer_norm(x, p[prefix + "norm2.scale"], p[prefix + "norm2.bias"], eps, sem)
     h = linear(h, p[prefix + "mlp.layers.0.kernel"], p[prefix + "mlp.layers.0.bias"], sem)
     h = _act(h, use_quick_gelu, sem)
     h = linear(h, p[prefix + "mlp.layers.3.kernel"], p[prefix + "mlp.layers.3.bias"], sem)
-    return x + h  # :131
+    return _out(x + h, sem)  # :131
 
 
 def transformer(p: Params, prefix: str, x, layers, num_heads, use_quick_gelu, mask=None, eps=1e-6, sem: Semantics = JIMM):
@@ -179,14 +201,14 @@ def transformer(p: Params, prefix: str, x, layers, num_heads, use_quick_gelu, ma
 def map_head(p: Params, prefix: str, x, num_heads, eps, sem: Semantics = JIMM):
     """MultiHeadAttentionPoolingHead.__call__ (common/vit.py:87-101)."""
     B = x.shape[0]
-    probe = p[prefix + "probe"].expand(B, -1, -1)  # :96
+    probe = _prm(p[prefix + "probe"], sem).expand(B, -1, -1)  # :96
     y = multi_head_attention(p, prefix + "attn.", probe, x, num_heads, None, sem)  # :97
     residual = y
-    y = layer_norm(y, p[prefix + "layernorm.scale"], p[prefix + "layernorm.bias"], eps)
+    y = layer_norm(y, p[prefix + "layernorm.scale"], p[prefix + "layernorm.bias"], eps, sem)
     h = linear(y, p[prefix + "mlp.layers.0.kernel"], p[prefix + "mlp.layers.0.bias"], sem)
-    h = torch.nn.functional.gelu(h) if sem.gelu == "erf" else gelu_tanh(h)  # nnx.gelu :75
+    h = torch.nn.functional.gelu(h) if sem.gelu == "erf" else _out(gelu_tanh(h), sem)  # nnx.gelu :75
     h = linear(h, p[prefix + "mlp.layers.2.kernel"], p[prefix + "mlp.layers.2.bias"], sem)
-    return (residual + h)[:, 0]  # :100-101
+    return _out(residual + h, sem)[:, 0]  # :100-101
 
 
 @dataclass
@@ -215,9 +237,9 @@ def patch_embed(p: Params, prefix: str, img, cfg: TowerCfg, sem: Semantics = JIM
     gh, gw = Hh // P, Ww // P
     x = img[:, : gh * P, : gw * P, :].reshape(B, gh, P, gw, P, C).permute(0, 1, 3, 2, 4, 5).reshape(B, gh * gw, P * P * C)
     K = p[prefix + "patch_embeddings.kernel"].reshape(P * P * C, -1)
-    y = round_operand(x, sem.operand_round) @ round_operand(K, sem.operand_round)
+    y = _out(round_operand(x, sem.operand_round) @ round_operand(K, sem.operand_round), sem)
     if cfg.use_patch_bias:
-        y = y + p[prefix + "patch_embeddings.bias"]
+        y = _out(y + _prm(p[prefix + "patch_embeddings.bias"], sem), sem)
     return y
 
 
@@ -228,15 +250,15 @@ def vision_tower(p: Params, prefix: str, img, cfg: TowerCfg, sem: Semantics = JI
     x = patch_embed(p, prefix, img, cfg, sem)
     B = x.shape[0]
     if cfg.pooling_type == "CLS":
-        cls = p[prefix + "cls_token"].expand(B, -1, -1)  # :232
+        cls = _prm(p[prefix + "cls_token"], sem).expand(B, -1, -1)  # :232
         x = torch.cat([cls, x], dim=1)  # :233
-    x = x + p[prefix + "position_embeddings"]  # :236
+    x = _out(x + _prm(p[prefix + "position_embeddings"], sem), sem)  # :236
     if cfg.use_pre_norm:
-        x = layer_norm(x, p[prefix + "ln_pre.scale"], p[prefix + "ln_pre.bias"], cfg.layernorm_epsilon)  # :239
+        x = layer_norm(x, p[prefix + "ln_pre.scale"], p[prefix + "ln_pre.bias"], cfg.layernorm_epsilon, sem)  # :239
     # dropout is identity in eval (:241)
     # NOTE quirk 2: the Transformer is built WITHOUT layernorm_epsilon (:193-204) -> block eps 1e-6
     x = transformer(p, prefix + "transformer.", x, cfg.num_layers, cfg.num_heads, cfg.use_quick_gelu, None, 1e-6, sem)
-    x = layer_norm(x, p[prefix + "ln_post.scale"], p[prefix + "ln_post.bias"], cfg.layernorm_epsilon)  # :244
+    x = layer_norm(x, p[prefix + "ln_post.scale"], p[prefix + "ln_post.bias"], cfg.layernorm_epsilon, sem)  # :244
     if cfg.pooling_type == "CLS":
         return x[:, 0]  # :246
     return map_head(p, prefix + "MAPHead.", x, cfg.num_heads, cfg.layernorm_epsilon, sem)  # :248
@@ -311,27 +333,29 @@ def clip_encode_image(p: Params, cfg: DualCfg, img, sem: Semantics = JIMM):
 def clip_encode_text(p: Params, cfg: DualCfg, text, sem: Semantics = JIMM):
     """CLIP.encode_text (models/clip.py:148-167)."""
     seq = text.shape[1]
-    x = p["token_embedding.embedding"][text]  # :159
-    x = x + p["positional_embedding"][:seq]  # :160
+    x = _prm(p["token_embedding.embedding"][text], sem)  # :159
+    x = _out(x + _prm(p["positional_embedding"][:seq], sem), sem)  # :160
     mask = torch.tril(torch.ones(cfg.context_length, cfg.context_length, dtype=x.dtype))  # :62
     x = transformer(p, "text_model.", x, cfg.transformer_layers, cfg.transformer_heads, True, mask, 1e-6, sem)  # :161 (eps not forwarded :92-104)
-    x = layer_norm(x, p["ln_final.scale"], p["ln_final.bias"], 1e-5)  # :162 (:117)
+    x = layer_norm(x, p["ln_final.scale"], p["ln_final.bias"], 1e-5, sem)  # :162 (:117)
     eot = text.argmax(dim=-1)  # :164
     x = x[torch.arange(x.shape[0]), eot]
-    return round_operand(x, sem.operand_round) @ round_operand(p["text_projection.kernel"], sem.operand_round)  # :166
+    return _out(round_operand(x, sem.operand_round) @ round_operand(p["text_projection.kernel"], sem.operand_round), sem)  # :166
 
 
-def contrastive_logits(img_f, txt_f, logit_scale, logit_bias=None):
-    """models/clip.py:183-187 / models/siglip.py:169-173 (no epsilon in the norms)."""
-    i = img_f / torch.linalg.norm(img_f, dim=-1, keepdim=True)
-    t = txt_f / torch.linalg.norm(txt_f, dim=-1, keepdim=True)
-    logits = (torch.exp(logit_scale) * i) @ t.T
-    return logits if logit_bias is None else logits + logit_bias
+def contrastive_logits(img_f, txt_f, logit_scale, logit_bias=None, sem: Semantics = JIMM):
+    """models/clip.py:183-187 / models/siglip.py:169-173 (no epsilon in the norms).  In flax-bf16 semantics the features
+    arrive as bf16 arrays, so the norm, the division, exp(logit_scale) and the matmul each return bf16."""
+    o_ = lambda t: _out(t, sem)
+    i = o_(img_f / o_(torch.linalg.norm(img_f, dim=-1, keepdim=True)))
+    t = o_(txt_f / o_(torch.linalg.norm(txt_f, dim=-1, keepdim=True)))
+    logits = o_(o_(o_(torch.exp(_prm(logit_scale, sem))) * i) @ t.T)
+    return logits if logit_bias is None else o_(logits + _prm(logit_bias, sem))
 
 
 def clip_forward(p: Params, cfg: DualCfg, img, text, sem: Semantics = JIMM):
     """CLIP.__call__ (models/clip.py:169-188)."""
-    return contrastive_logits(clip_encode_image(p, cfg, img, sem), clip_encode_text(p, cfg, text, sem), p["logit_scale"])
+    return contrastive_logits(clip_encode_image(p, cfg, img, sem), clip_encode_text(p, cfg, text, sem), p["logit_scale"], None, sem)
 
 
 def siglip_encode_image(p: Params, cfg: DualCfg, img, sem: Semantics = JIMM):
@@ -342,17 +366,17 @@ def siglip_encode_image(p: Params, cfg: DualCfg, img, sem: Semantics = JIMM):
 def siglip_encode_text(p: Params, cfg: DualCfg, text, sem: Semantics = JIMM):
     """SigLIP.encode_text (models/siglip.py:135-153)."""
     seq = text.shape[1]
-    x = p["token_embedding.embedding"][text]
-    x = x + p["positional_embedding"][:seq]
+    x = _prm(p["token_embedding.embedding"][text], sem)
+    x = _out(x + _prm(p["positional_embedding"][:seq], sem), sem)
     x = transformer(p, "text_model.", x, cfg.transformer_layers, cfg.transformer_heads, False, None, 1e-6, sem)  # :81-92 eps 1e-6
-    x = layer_norm(x, p["ln_final.scale"], p["ln_final.bias"], 1e-6)  # :104
+    x = layer_norm(x, p["ln_final.scale"], p["ln_final.bias"], 1e-6, sem)  # :104
     return linear(x[:, -1, :], p["text_projection.kernel"], p["text_projection.bias"], sem)  # :151-152
 
 
 def siglip_forward(p: Params, cfg: DualCfg, img, text, sem: Semantics = JIMM):
     """SigLIP.__call__ (models/siglip.py:155-174)."""
     return contrastive_logits(siglip_encode_image(p, cfg, img, sem), siglip_encode_text(p, cfg, text, sem),
-                              p["logit_scale"], p["logit_bias"])
+                              p["logit_scale"], p["logit_bias"], sem)
 
 
 # --------------------------------------------------------------------------- #

@@ -47,3 +47,36 @@ def quick_gelu(x):
 
 def rel_err(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+# ---- parity bookkeeping: every parity assertion records (config, dtype, bound, achieved) so a pass at 1.9e-3 and a pass at
+#      1e-5 do not look alike.  Records go to gpurun_out/parity_records.jsonl (merged back from the GPU box) and are turned into
+#      the committed PARITY.md by scripts/make_parity_md.py.
+import json
+import os
+import time
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PARITY_LOG = os.environ.get("JIMM_PARITY_LOG", os.path.join(_ROOT, "gpurun_out", "parity_records.jsonl"))
+
+
+def record_parity(case: str, what: str, dtype: str, against: str, bound, achieved: float, **extra):
+    rec = dict(case=case, what=what, dtype=dtype, against=against, bound=bound, achieved=float(achieved), ok=bool(bound is None or achieved < bound),
+               t=time.strftime("%Y-%m-%dT%H:%M:%S"), **extra)
+    try:
+        os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+        with open(PARITY_LOG, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    except OSError:
+        pass
+    return rec
+
+
+def check_parity(case: str, what: str, dtype, against: str, out, ref, bound, **extra) -> float:
+    """rel = max|out - ref| / max|ref|; recorded, then asserted against `bound` (None = report only)."""
+    r = rel_err(torch.as_tensor(out).detach().cpu(), torch.as_tensor(ref).detach().cpu())
+    dn = str(dtype).replace("torch.", "")
+    record_parity(case, what, dn, against, bound, r, **extra)
+    if bound is not None:
+        assert r < bound, f"{case}/{what} [{dn}] vs {against}: rel err {r:.3e} >= bound {bound:.1e}"
+    return r
