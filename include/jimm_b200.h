@@ -99,6 +99,12 @@ JIMM_API int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, i
 JIMM_API int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream);
 JIMM_API int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int Bi, const int32_t* ids_host, int Bt, int T,
                            float* logits_host, void* stream);
+/* The whole examples/vit_inference.py:27-58 pipeline from raw frames: host uint8 RGB [B,H,W,3] -> (bytes over PCIe, a quarter of the
+ * fp32 pixel values) -> image front-end `pre` on the GPU (see jimm_preproc_* below; its output size must equal the model's input) ->
+ * tower -> host fp32 [B, num_classes | v_width].  Same slicing / stream semantics as jimm_vit_forward_host. */
+typedef struct jimm_preproc jimm_preproc_t;
+JIMM_API int jimm_vit_forward_host_u8(jimm_model_t* m, jimm_preproc_t* pre, const uint8_t* img_host, int B, int H, int W, float* out_host,
+                                      void* stream);
 
 /* -- multi-GPU contrastive head: one process per GPU, embeddings exchanged over NVLink peer memory ------------------- */
 /* Allocate this rank's symmetric gather buffer ([world*max_rows, 2E] fp32 + flags) and export its IPC handle
@@ -136,7 +142,6 @@ JIMM_API int jimm_k_logits(const float* img, const float* txt, const float* logi
  * normalise, written NHWC in the dtype the tower consumes.  Bit-exact with that pipeline (integer resampling, IEEE fp32
  * rescale/normalise).  Mirrors `preprocessor_config.json`: size {height,width} | {shortest_edge}, crop_size, resample,
  * rescale_factor, image_mean, image_std. */
-typedef struct jimm_preproc jimm_preproc_t;
 typedef struct jimm_preproc_config {
   int height, width;        /* exact output size (ViT, SigLIP: size = {height, width}) ... */
   int shortest_edge;        /* ... or, when non-zero, resize the shortest edge to this keeping the aspect ratio (CLIP) */

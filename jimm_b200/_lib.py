@@ -65,6 +65,7 @@ SIGNATURES = {
     "jimm_dual_forward": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),
     "jimm_vit_forward_host": (_i, [_vp, _vp, _i, _i, _fp, _vp]),
     "jimm_dual_forward_host": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),
+    "jimm_vit_forward_host_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _vp]),
     "jimm_comm_init": (_i, [_vp, _i, _i, _i, C.c_char_p]),
     "jimm_comm_connect": (_i, [_vp, C.c_char_p]),
     "jimm_comm_contrastive_logits": (_i, [_vp, _fp, _fp, _i, _fp, _vp]),

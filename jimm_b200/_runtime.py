@@ -76,6 +76,7 @@ class NativeModel:
         _lib.check(self.lib.jimm_model_output_dim(self.handle, C.byref(vo), C.byref(to)))
         self.vision_out, self.text_out = vo.value, to.value
         self._comm = None
+        self.preproc = None  # ImagePreprocessor for uint8 inputs (set by the owning model's set_preprocessor)
 
     def side_stream(self) -> torch.cuda.Stream:
         """Copy stream for host inputs of the multi-GPU dual path."""
@@ -100,6 +101,17 @@ class NativeModel:
         if x.ndim != 4:
             raise ValueError(f"expected images of shape [batch, height, width, channels], got {tuple(x.shape)}")
         c = self.cfg
+        if x.dtype == torch.uint8:
+            # raw RGB frames: need the attached image front-end (model.set_preprocessor); any frame size it maps to the model's input
+            if self.preproc is None:
+                raise ValueError("uint8 images need an image front-end: call model.set_preprocessor(ImagePreprocessor...) first, "
+                                 "or pass normalised float pixel values")
+            if x.shape[3] != 3:
+                raise ValueError(f"expected uint8 RGB frames [B,H,W,3], got {tuple(x.shape)}")
+            oh, ow = self.preproc.output_size(x.shape[1], x.shape[2])
+            if (oh, ow) != (c.img_size, c.img_size):
+                raise ValueError(f"the image front-end maps {x.shape[1]}x{x.shape[2]} frames to {oh}x{ow}, the model takes {c.img_size}x{c.img_size}")
+            return x.contiguous()
         if x.shape[1] != c.img_size or x.shape[2] != c.img_size or x.shape[3] != c.in_ch:
             raise ValueError(f"expected NHWC images [B,{c.img_size},{c.img_size},{c.in_ch}], got {tuple(x.shape)}")
         if x.dtype not in _TORCH_TO_CODE:
@@ -119,6 +131,8 @@ class NativeModel:
         B = x.shape[0]
         fn_dev = self.lib.jimm_encode_image if encode else self.lib.jimm_vit_forward
         if x.is_cuda:
+            if x.dtype == torch.uint8:  # device frames: front-end kernel, then the tower, on the current stream
+                x = self.preproc(x, dtype=self._operand_dtype())
             with torch.cuda.device(self.device):
                 out = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
                 _lib.check(fn_dev(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(out.data_ptr()),
@@ -135,6 +149,9 @@ class NativeModel:
             return PendingResult(self.vision(x, encode), None)
         return self._vision_host(x, encode)
 
+    def _operand_dtype(self) -> torch.dtype:
+        return {_lib.F32: torch.float32, _lib.F16: torch.float16, _lib.BF16: torch.bfloat16}[self.cfg.compute_dtype]
+
     def _vision_host(self, x: torch.Tensor, encode: bool) -> "PendingResult":
         B = x.shape[0]
         fn_dev = self.lib.jimm_encode_image if encode else self.lib.jimm_vit_forward
@@ -144,8 +161,14 @@ class NativeModel:
             # intra-op OpenMP team on a CPU-quota-limited box costs milliseconds
             out = torch.empty((B, self.vision_out), dtype=torch.float32, pin_memory=True)
             cur = torch.cuda.current_stream(self.device)
-            if encode:
+            if x.dtype == torch.uint8 and not encode:
+                # raw frames: bytes over PCIe, front-end + tower in the library's sliced copy/compute pipeline
+                _lib.check(self.lib.jimm_vit_forward_host_u8(self.handle, self.preproc.handle, C.c_void_p(x.data_ptr()), B, x.shape[1], x.shape[2],
+                                                             C.c_void_p(out.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+            elif encode:
                 xd = x.to(self.device, non_blocking=True)
+                if xd.dtype == torch.uint8:
+                    xd = self.preproc(xd, dtype=self._operand_dtype())
                 od = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
                 _lib.check(fn_dev(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(od.data_ptr()),
                                   C.c_void_p(_stream_ptr(self.device))))

@@ -39,6 +39,7 @@ class _NativeOwner:
 
     def _native_init(self, dtype):
         object.__setattr__(self, "_native", None)
+        object.__setattr__(self, "_preproc", None)
         object.__setattr__(self, "_compute_dtype", nn.compute_dtype_code(dtype))
         object.__setattr__(self, "_max_batch", default_max_batch())
 
@@ -61,8 +62,18 @@ class _NativeOwner:
             n.close()
         mb = max(self._max_batch, int(batch) if require else 1)
         n = NativeModel(self._native_config(), self.flat_params(), mb)
+        n.preproc = self._preproc
         object.__setattr__(self, "_native", n)
         return n
+
+    def set_preprocessor(self, preprocessor):
+        """Attach a `jimm_b200.preprocess.ImagePreprocessor`: the model then also accepts raw uint8 RGB frames [B,H,W,3] (host or
+        CUDA) -- examples/vit_inference.py:27-37's `processor(images=...)` + transpose runs on the GPU, and host batches cross PCIe
+        as bytes instead of fp32 pixel values."""
+        object.__setattr__(self, "_preproc", preprocessor)
+        if self._native is not None:
+            self._native.preproc = preprocessor
+        return self
 
     def set_max_batch(self, max_batch: int):
         """Bound of samples per native call (workspace is sized for it at finalize)."""

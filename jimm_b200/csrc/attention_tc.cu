@@ -2,18 +2,21 @@
 //
 //   o[b*S+s, h*64+d] = softmax_k((q/8) k^T  masked) v            nnx.MultiHeadAttention core, common/transformer.py:130
 //
-// Every jimm tower with S <= 256 lands here (ViT-B/16@224: 197, SigLIP-B/16@256: 256, CLIP-B/32: 50 / 77 causal); longer
-// sequences use the flash kernel in attention.cu.  With S <= 256 a whole score row fits one TMEM accumulator, so there is
-// no online-softmax rescaling: one persistent CTA per SM loops over (sample, head) items:
+// Every jimm tower with S <= 256 lands here (ViT-B/16@224: 197, SigLIP-B/16@256: 256, CLIP-B/32: 50 / 77 causal, SigLIP text: 64);
+// longer sequences use attention_tc_long.cu.  With S <= 256 a whole score row fits one TMEM accumulator, so there is no
+// online-softmax rescaling.  One persistent CTA per SM loops over (sample, head) ITEMS; the work UNIT is one 128-row query tile of an
+// item (one or two per item).  Units alternate between two TMEM slots / softmax warp groups and run as two DECOUPLED streams: while
+// one group is in its softmax (MUFU / issue bound), the other slot is in its tensor phase (P V, O read-out, next Q K^T), so the
+// stage latencies of a unit overlap with the other stream instead of adding up (round 1 ran both tiles of an item in lock-step:
+// 110 us per ViT-B/16 layer; the stages of an item were serial, profiles/r1_d).
 //
-//   warp 0   TMA: Q, K, V of the item (three 256 x 128 B boxes of the fused qkv buffer, SWIZZLE_128B), 2-deep ring
-//   warp 1   MMA: S_t = Q_t K^T  (tcgen05.mma SS, M=128, N=ceil16(S), K=64) for the one or two 128-row query tiles t,
-//                 then O_t = P_t V (tcgen05.mma with A = P_t read from TENSOR MEMORY, B = V as an MN-major smem operand)
-//   warp 2   TMEM allocator (512 columns: tile t owns columns [256t, 256t+256): S, overwritten in place by fp16/bf16 P in
+//   warp 0   TMA: Q, K, V of the item (three `rows` x 128 B boxes of the fused qkv buffer, SWIZZLE_128B), ring of 2-4 items
+//   warp 1   MMA issuer, software pipelined over units u:  Q K^T(u) -> P V(u-1) -> Q K^T(u+1) -> P V(u) ...
+//            S_u = Q_t K^T (tcgen05.mma SS, M=128, N=ceil16(S), K=64); O_u = P_u V (A = P_u read from TENSOR MEMORY, B = V MN-major)
+//   warp 2   TMEM allocator (512 columns: slot g = u & 1 owns columns [256g, 256g+256): S, overwritten in place by fp16/bf16 P in
 //            the first N/2 columns, O in columns 128..191)
-//   warps 4-11  softmax + output, one group of 4 warps per query tile, thread = query row: pass 1 row max from TMEM,
-//            pass 2 exp2 / row sum / pack / tcgen05.st P, then O * (1/l) -> global after the P V MMA.
-// Measured bound: TMEM read bandwidth (~64 B/clk/SM), hence the single pass over S with a lazily raised reference maximum.
+//   warps 4-11  softmax + output, group g = 4 warps per slot, thread = query row: one pass exp2 / row sum / pack / tcgen05.st P with a
+//            lazily raised reference maximum, then O * (1/l) -> smem -> 3-D TMA store after the P V MMA.
 #include <type_traits>
 
 #include "common.cuh"
@@ -22,10 +25,9 @@
 namespace jimm {
 
 static constexpr int ATC_THREADS = 384;
-static constexpr int ATC_TILE_BYTES = 256 * 128;                 // one Q / K / V box
-static constexpr int ATC_BUF_BYTES = 3 * ATC_TILE_BYTES;          // 96 KB per item
 static constexpr int ATC_OBUF_BYTES = 8 * 32 * 128;                // one 32 x 128 B store box per softmax warp
-static constexpr int ATC_SMEM = 2 * ATC_BUF_BYTES + ATC_OBUF_BYTES + 256 + 1024;
+static constexpr int ATC_MAX_BUFS = 4;                             // item ring depth (Q, K, V boxes of `rows` rows each)
+static constexpr int ATC_SMEM_BUDGET = 232448 - ATC_OBUF_BYTES - 256 - 1024;  // bytes left for the item ring
 
 // multiply a packed pair of 16-bit values by f (rare lazy-rescale path)
 template <typename T>
@@ -43,6 +45,8 @@ struct AtcParams {
   int B, S, H, D;
   int nq;       // query tiles per item (1 or 2)
   int Nk;       // keys rounded up to 16 (MMA N of S = Q K^T, MMA K of O = P V)
+  int rows;     // rows of one Q / K / V box (>= S, multiple of 8): the item buffer is 3 * rows * 128 bytes
+  int nbuf;     // item buffers in the smem ring (2 .. ATC_MAX_BUFS)
   float scale_log2;
   void* out;
   int reverse;  // walk the (sample, head) items from the end (see kernels.cuh)
@@ -54,18 +58,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   constexpr uint32_t FMT = std::is_same<T, __half>::value ? 0u : 1u;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* obuf_base = smem + 2 * ATC_BUF_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * ATC_BUF_BYTES + ATC_OBUF_BYTES);
-  uint64_t* kv_full = bars;        // [2]
-  uint64_t* kv_empty = bars + 2;   // [2]
-  uint64_t* s_full = bars + 4;     // [2] per query tile
-  uint64_t* p_ready = bars + 6;    // [2]
-  uint64_t* o_full = bars + 8;     // [2]
-  uint64_t* slot_free = bars + 10; // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  const int tile_bytes = p.rows * 128;   // one Q / K / V box
+  const int item_bytes = 3 * tile_bytes;  // multiple of 1024 (rows % 8 == 0)
+  uint8_t* obuf_base = smem + p.nbuf * item_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(obuf_base + ATC_OBUF_BYTES);
+  uint64_t* kv_full = bars;                      // [ATC_MAX_BUFS]
+  uint64_t* kv_empty = bars + ATC_MAX_BUFS;      // [ATC_MAX_BUFS]
+  uint64_t* s_full = bars + 2 * ATC_MAX_BUFS;    // [2] per TMEM slot
+  uint64_t* p_ready = s_full + 2;                // [2]
+  uint64_t* o_full = s_full + 4;                 // [2]
+  uint64_t* slot_free = s_full + 6;              // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_full + 8);
 
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_items = p.B * p.H;
+  const int my_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int my_units = my_items * p.nq;
 
   pdl_launch_dependents();
   if (warp_idx == 0 && lane == 0) {
@@ -73,9 +81,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
     tma_prefetch_desc(&map_out);
   }
   if (warp_idx == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ATC_MAX_BUFS; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 4);
       mbar_init(&o_full[i], 1);
@@ -93,84 +103,96 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      int buf = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_items; ++it) {
+        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
         const int ie = p.reverse ? num_items - 1 - item : item;
         const int b = ie / p.H, h = ie - b * p.H;
-        const int buf = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        uint8_t* base = smem + buf * ATC_BUF_BYTES;
+        uint8_t* base = smem + buf * item_bytes;
         mbar_wait(&kv_empty[buf], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[buf], ATC_BUF_BYTES);
+        mbar_arrive_expect_tx(&kv_full[buf], item_bytes);
         const int row0 = b * p.S;
         tma_load_2d(base, &map_qkv, &kv_full[buf], h * 64, row0);
-        tma_load_2d(base + ATC_TILE_BYTES, &map_qkv, &kv_full[buf], p.D + h * 64, row0);
-        tma_load_2d(base + 2 * ATC_TILE_BYTES, &map_qkv, &kv_full[buf], 2 * p.D + h * 64, row0);
+        tma_load_2d(base + tile_bytes, &map_qkv, &kv_full[buf], p.D + h * 64, row0);
+        tma_load_2d(base + 2 * tile_bytes, &map_qkv, &kv_full[buf], 2 * p.D + h * 64, row0);
+        if (++buf == p.nbuf) { buf = 0; ph ^= 1; }
       }
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     {
       // The whole warp runs this control flow (waits, counters and descriptors stay warp-uniform, i.e. in uniform registers); only the
-      // elected lane issues the tcgen05 instructions.  With 16 small MMAs per item the issue cost matters (long kernel: -4 %).
+      // elected lane issues the tcgen05 instructions.
       const bool leader = lane == 0;
       const uint32_t idesc_qk = make_idesc(FMT, 128, static_cast<uint32_t>(p.Nk), 0);
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint32_t ph = (it >> 1) & 1, sp = it & 1;
-        const uint32_t q_addr = smem_u32(smem + buf * ATC_BUF_BYTES);
+      const int nkk = p.Nk / 16;
+      // P V of unit v (slot v & 1, k-th use of that slot k = v >> 1), reading V from item buffer vbuf; `last` = last unit of its item
+      auto issue_pv = [&](int v, int vbuf, bool last) {
+        const int g = v & 1;
+        mbar_wait(&p_ready[g], static_cast<uint32_t>(v >> 1) & 1u);
+        tcgen05_fence_after();
+        if (leader) {
+          const uint64_t vdesc = make_umma_desc_sw128(smem_u32(smem + vbuf * item_bytes + 2 * tile_bytes));
+          for (int kk = 0; kk < nkk; ++kk)
+            umma_ts_f16(tmem_base + g * 256 + 128, tmem_base + g * 256 + kk * 8, vdesc + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
+                        kk > 0 ? 1u : 0u);
+          tcgen05_commit(&o_full[g]);
+          if (last) tcgen05_commit(&kv_empty[vbuf]);  // every MMA reading this item's smem has retired
+        }
+      };
+      int buf = 0, un = 0, prev_buf = 0;
+      uint32_t ph = 0;
+      bool prev_last = false;
+      for (int it = 0; it < my_items; ++it) {
+        const uint32_t q_addr = smem_u32(smem + buf * item_bytes);
         // descriptors advance by (bytes >> 4) in their address field: 32 B per 16-element K step, 2048 B per 16 keys of V
-        const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + ATC_TILE_BYTES),
-                       vdesc = make_umma_desc_sw128(q_addr + 2 * ATC_TILE_BYTES);
+        const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + tile_bytes);
         mbar_wait(&kv_full[buf], ph);
         tcgen05_fence_after();
-        for (int t = 0; t < p.nq; ++t) {
-          mbar_wait(&slot_free[t], sp ^ 1);  // the previous item's O of this tile has been read out
+        for (int t = 0; t < p.nq; ++t, ++un) {
+          const int g = un & 1;
+          mbar_wait(&slot_free[g], (static_cast<uint32_t>(un >> 1) & 1u) ^ 1u);  // the previous unit of this slot has been read out
           tcgen05_fence_after();
           if (leader) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_ss<0>(tmem_base + t * 256, qdesc + static_cast<uint64_t>(t * (16384 >> 4) + k * 2), kdesc + static_cast<uint64_t>(k * 2), idesc_qk,
+              umma_ss<0>(tmem_base + g * 256, qdesc + static_cast<uint64_t>(t * (16384 >> 4) + k * 2), kdesc + static_cast<uint64_t>(k * 2), idesc_qk,
                          k > 0 ? 1u : 0u);
-            tcgen05_commit(&s_full[t]);
+            tcgen05_commit(&s_full[g]);
           }
+          if (un > 0) issue_pv(un - 1, prev_buf, prev_last);  // the other stream's tensor phase, under this unit's softmax
+          prev_buf = buf;
+          prev_last = t == p.nq - 1;
         }
-        for (int t = 0; t < p.nq; ++t) {
-          mbar_wait(&p_ready[t], sp);
-          tcgen05_fence_after();
-          if (leader) {
-            for (int kk = 0; kk < p.Nk / 16; ++kk)
-              umma_ts_f16(tmem_base + t * 256 + 128, tmem_base + t * 256 + kk * 8, vdesc + static_cast<uint64_t>(kk * (2048 >> 4)), idesc_pv,
-                          kk > 0 ? 1u : 0u);
-            tcgen05_commit(&o_full[t]);
-          }
-        }
-        if (leader) tcgen05_commit(&kv_empty[buf]);  // every MMA reading this item's smem has retired
+        if (++buf == p.nbuf) { buf = 0; ph ^= 1; }
       }
+      if (un > 0) issue_pv(un - 1, prev_buf, prev_last);
     }
   } else if (warp_idx >= 4) {
     // ===================== softmax + output =====================
     const int q = warp_idx & 3;        // TMEM lane quarter
-    const int t = (warp_idx - 4) >> 2; // query tile
-    if (t < p.nq) {
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 256;
+    const int g = (warp_idx - 4) >> 2; // softmax group == TMEM slot: units g, g+2, g+4, ...
+    {
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 256;
       uint8_t* obuf = obuf_base + (warp_idx - 4) * (32 * 128);
-      const int row = t * 128 + q * 32 + lane;  // query index inside the sample
       const int S = p.S;
-      int kmax = S;  // number of keys this row attends to
-      if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
-      // warp-uniform upper bound of keys any row of this warp needs (rows >= S are clamped: finite garbage, never stored)
-      const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
-      const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
-      const int n_chunks = (p.Nk + 31) / 32, n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
-      int it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      const int n_chunks = (p.Nk + 31) / 32;
+      for (int un = g; un < my_units; un += 2) {
+        const int it = p.nq == 2 ? un >> 1 : un, t = p.nq == 2 ? un & 1 : 0;
+        const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
         const int ie = p.reverse ? num_items - 1 - item : item;
         const int b = ie / p.H, h = ie - b * p.H;
-        const uint32_t sp = it & 1;
-        mbar_wait(&s_full[t], sp);
+        const uint32_t sp = static_cast<uint32_t>(un >> 1) & 1u;  // k-th use of this slot
+        const int row = t * 128 + q * 32 + lane;  // query index inside the sample
+        int kmax = S;  // number of keys this row attends to
+        if (CAUSAL) kmax = row + 1 < S ? row + 1 : S;
+        // warp-uniform upper bound of keys any row of this warp needs (rows >= S are clamped: finite garbage, never stored)
+        const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
+        const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
+        const int n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
+        mbar_wait(&s_full[g], sp);
         tcgen05_fence_after();
         // ---- single pass over S (the kernel is bound by TMEM read bandwidth, ~64 B/clk/SM: reading the scores twice for an
         //      exact row max first cost 45 % more; profiles/r1_d).  Lazy-rescale softmax: p = exp2((s - m_ref) * scale) against a
@@ -258,10 +280,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[t]);
+        if (lane == 0) mbar_arrive(&p_ready[g]);
         // ---- output: O / l ----
         const float inv = 1.0f / l;
-        mbar_wait(&o_full[t], sp);
+        mbar_wait(&o_full[g], sp);
         tcgen05_fence_after();
         uint32_t o0[32], o1[32];
         tmem_ld_32x32b_x32(taddr + 128, o0);
@@ -269,7 +291,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&slot_free[t]);  // TMEM of this tile may be overwritten by the next item's S
+        if (lane == 0) mbar_arrive(&slot_free[g]);  // TMEM of this slot may be overwritten by its next unit's S
         // O tile rows -> swizzled 32 x 128 B box in smem -> 3-D TMA store (rows >= S are clipped by the [B, S, D] tensor map;
         // the row-per-thread 16-byte global stores this replaces cost 32 LSU wavefronts per instruction)
         {
@@ -323,36 +345,41 @@ int make_tensor_map_3d(CUtensorMap* map, int dtype, const void* ptr, int B, int 
 template <typename T, typename OutT>
 static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   const int D = H * 64;
-  CUtensorMap map;
-  if (int rc = make_tensor_map_2d(&map, io_type, qkv, B * S, 3 * D, 3 * D, 256)) return rc;
-  CUtensorMap map_out;
-  if (int rc = make_tensor_map_3d(&map_out, out_type, out, B, S, D, D)) return rc;
   AtcParams p;
   p.B = B; p.S = S; p.H = H; p.D = D;
   p.nq = (S + 127) / 128;
   p.Nk = ((S + 15) / 16) * 16;
+  // Box rows: the keys the MMAs read (Nk) -- for two query tiles the second Q tile reads rows 128..255 of the Q box, rows past the box
+  // land in the K box of the same item buffer (finite or not, they only feed query rows >= S, which the output map clips).
+  p.rows = p.Nk;
+  const int item_bytes = 3 * p.rows * 128;
+  p.nbuf = ATC_SMEM_BUDGET / item_bytes;
+  if (p.nbuf > ATC_MAX_BUFS) p.nbuf = ATC_MAX_BUFS;
+  if (p.nbuf < 2) { set_last_error("attention_tc: item of %d bytes does not fit a 2-deep ring", item_bytes); return -1; }
+  const int smem_bytes = p.nbuf * item_bytes + ATC_OBUF_BYTES + 256 + 1024;
+  CUtensorMap map;
+  if (int rc = make_tensor_map_2d(&map, io_type, qkv, B * S, 3 * D, 3 * D, p.rows)) return rc;
+  CUtensorMap map_out;
+  if (int rc = make_tensor_map_3d(&map_out, out_type, out, B, S, D, D)) return rc;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = out;
   p.reverse = reverse;
   const int items = B * H;
   const int grid = items < device_sm_count() ? items : device_sm_count();
-  static bool attr_set = false;
-  if (!attr_set) {
-    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
-    attr_set = true;
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_kernel<T, OutT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
   }
-  if (causal) JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, true>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, map_out, p));
-  else JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, false>, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, 1, true, map, map_out, p));
+  if (causal) JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, true>, dim3(grid), dim3(ATC_THREADS), smem_bytes, stream, 1, true, map, map_out, p));
+  else JIMM_CUDA_CHECK(launch_k(attention_tc_kernel<T, OutT, false>, dim3(grid), dim3(ATC_THREADS), smem_bytes, stream, 1, true, map, map_out, p));
   note_launch();
   return 0;
 }
 
-// Returns 1 when this configuration is not handled here (caller falls back to the flash kernel).
+// Returns 1 when this configuration is not handled here (caller falls back to attention.cu / attention_tc_long.cu).
 int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
-  // One query tile (S <= 128) leaves half of the softmax warps idle: the flash kernel is as fast or faster there (measured:
-  // S=50 39 us vs 25 us, S=77 causal 35 vs 37 us; S=197 128 vs 218 us, S=256 140 vs 215 us at B=256).
-  if (S > 256 || S <= 128) return 1;
+  if (S > 256 || S < 1) return 1;
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
   if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
   if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);

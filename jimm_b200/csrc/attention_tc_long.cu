@@ -366,10 +366,9 @@ static int atl_launch(const void* qkv, int io_type, void* out, int B, int S, int
   p.reverse = reverse;
   const long long units = static_cast<long long>(B) * H * p.n_qp;
   const int grid = units < device_sm_count() ? static_cast<int>(units) : device_sm_count();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(attention_tc_long_kernel<T, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATL_SMEM));
-    attr_set = true;
   }
   JIMM_CUDA_CHECK(launch_k(attention_tc_long_kernel<T, OutT>, dim3(grid), dim3(ATL_THREADS), ATL_SMEM, stream, 1, true, map_q, map_kv, p));
   note_launch();

@@ -62,6 +62,22 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Per-device one-shot flag: function attributes (cudaFuncSetAttribute) and device properties are PER DEVICE, while a process may
+// hold models on several GPUs (jimm_model_create takes a device index); a process-wide `static bool` would leave the second GPU's
+// kernels without their > 48 KB dynamic shared memory opt-in.
+struct DeviceOnce {
+  static constexpr int kMaxDevices = 64;
+  bool done[kMaxDevices] = {};
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // ----------------------------------------------------------------------------
 // device helpers
 // ----------------------------------------------------------------------------
@@ -189,6 +205,16 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Arrive without memory-ordering semantics: for barriers that only hand TENSOR MEMORY back to the MMA issuer.  The tcgen05.ld's are
+// complete (tcgen05.wait::ld) and ordered by tcgen05.fence::before_thread_sync; the default .release arrive additionally drains
+// every outstanding shared / global access of the thread (MEMBAR.ALL.CTA + ERRBAR in SASS: 20 % of all stall samples of the GEMM
+// epilogue warps, profiles/r2_a), which the accumulator hand-off does not need.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // CTA-pair TMA load: data lands in THIS CTA's smem, completion bytes are credited to the mbarrier at `mbar_cluster_addr`
 // (the leader CTA's barrier).

@@ -140,20 +140,26 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 
 // ---- TMA epilogue for one 128 x 128 half-tile owned by one epilogue warp's lane quarter (thread = row) ------------
 // 16-bit outputs: 64 columns per 32 x 128 B box (two x32 TMEM loads); 32-bit outputs: 32 columns per box.
-template <int OUT, int ACT, int NBUF>
+// `release()` hands the accumulator back to the MMA issuer; it is called as soon as this warp's LAST tcgen05.ld has completed, i.e.
+// before the math / staging / store of the last box (the data is in registers by then), not after the whole epilogue.
+template <int OUT, int ACT, int NBUF, typename Release>
 __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const EpiDev& epi, uint32_t taddr, const float* sbias, uint8_t* tbuf0,
-                                             int lane, int row_base, int n_tile0, int c_begin, uint32_t& box_count) {
+                                             int lane, int row_base, int n_tile0, int c_begin, uint32_t& box_count, Release&& release) {
   constexpr bool OUT16 = (OUT == OUT_H16 || OUT == OUT_BF16);
   constexpr int COLS_PER_BOX = OUT16 ? 64 : 32;
   const int N = epi.N;
   uint32_t r[32], r2[32], pk[32];
+  bool released = false;
   if (n_tile0 + c_begin < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
 #pragma unroll 1
   for (int c = c_begin; c < c_begin + BN / 2; c += COLS_PER_BOX) {
     const int n0 = n_tile0 + c;
     if (n0 >= N) break;
+    const int cn = c + COLS_PER_BOX;
+    const bool more = (cn < c_begin + BN / 2) && (n_tile0 + cn < N);
     tmem_ld_wait();
     if constexpr (OUT16) tmem_ld_32x32b_x32(taddr + c + 32, r2);  // second half of this box, in flight during the math below
+    else if (!more) { release(); released = true; }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
       const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + j);
@@ -169,11 +175,10 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
         pk[j] = __float_as_uint(v0); pk[j + 1] = __float_as_uint(v1); pk[j + 2] = __float_as_uint(v2); pk[j + 3] = __float_as_uint(v3);
       }
     }
-    const int cn = c + COLS_PER_BOX;
-    const bool more = (cn < c_begin + BN / 2) && (n_tile0 + cn < N);
     if constexpr (OUT16) {
       tmem_ld_wait();
       if (more) tmem_ld_32x32b_x32(taddr + cn, r);  // prefetch the next box
+      else { release(); released = true; }
 #pragma unroll
       for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + 32 + j);
@@ -213,6 +218,7 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
       tma_store_commit();
     }
   }
+  if (!released) release();
 }
 
 // ---- generic LSU epilogue (4 warps; run-time flags; modes 0 = staged / 1 = direct) ---------------------------------
@@ -456,20 +462,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      // hand the accumulator back: all of this warp's tcgen05.ld's of the tile are complete (wait::ld) when this runs
+      auto release = [&]() {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster_relaxed(tmem_empty_leader0 + acc * 8);
+          else mbar_arrive_relaxed(&tmem_empty_bar[acc]);
+        }
+      };
       if (dbg_no_epi) {
+        release();
       } else if constexpr (OUT != OUT_GENERIC) {
         if (row_base < M)
           epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES, lane, row_base, n_blk * BN,
-                                           half * (BN / 2), box_count);
+                                           half * (BN / 2), box_count, release);
+        else
+          release();
       } else {
         if (half == 0 && row_base < M)
           epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_blk * BN);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_cluster(tmem_empty_leader0 + acc * 8);
-        else mbar_arrive(&tmem_empty_bar[acc]);
+        release();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -587,16 +600,19 @@ int make_tensor_map_2d(CUtensorMap* map, int dtype, const void* ptr, int rows, i
   return make_map(map, dtype, ptr, rows, cols, ld, box_rows);
 }
 
-int device_sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+int device_sm_count() {  // of the CURRENT device (cached per device: a process may drive several GPUs)
+  static int sms[DeviceOnce::kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= DeviceOnce::kMaxDevices) dev = 0;
+  if (sms[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     const char* env = getenv("JIMM_NUM_SMS");
-    if (env && atoi(env) > 0) sms = atoi(env);
+    if (env && atoi(env) > 0) n = atoi(env);
+    sms[dev] = n;
   }
-  return sms;
+  return sms[dev];
 }
 
 static int check_epi(const GemmEpilogue& e, int N) {
@@ -664,11 +680,10 @@ static int pair_mode_enabled() {
 
 template <typename T, int OUT, int ACT>
 static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (attr_set.first()) {
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   const int n_tiles = (p->N + BN - 1) / BN;
   const EpiDev d = to_dev(p->epi, M, p->N);

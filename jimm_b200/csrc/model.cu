@@ -154,6 +154,8 @@ struct Workspace {
   float* nrm_i = nullptr; // normalised
   float* nrm_t = nullptr;
   void* in_img = nullptr; // host-path staging: image batch (fp32 worst case)
+  uint8_t* in_u8 = nullptr;  // host-path staging of raw uint8 RGB frames (jimm_vit_forward_host_u8); grown on demand
+  size_t in_u8_bytes = 0;
   int32_t* in_ids = nullptr;
   float* out_dev = nullptr;  // host-path staging for results
   size_t out_dev_elems = 0;
@@ -188,6 +190,7 @@ struct jimm_model {
   bool host_chain = false;            // the last toucher of the staging buffer was jimm_vit_forward_host ...
   cudaStream_t host_chain_stream = nullptr;  // ... on this stream ...
   int host_chain_sizes[kHostSlices] = {};    // ... with this slice layout
+  int host_chain_kind = 0;                   // ... 0: float images into in_img, 1: uint8 frames into in_u8 (+ front-end into in_img)
   bool slot_recorded[kHostSlices] = {};
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -850,6 +853,7 @@ int jimm_model_destroy(jimm_model_t* m) {
     for (int i = 0; i < jimm_model::kHostSlices; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_consumed[i]); }
     cudaEventDestroy(m->ev_start);
   }
+  if (m->ws.in_u8) cudaFree(m->ws.in_u8);
   m->pool.release();
   delete m;
   return 0;
@@ -980,24 +984,36 @@ static void host_slices(const jimm_model* m, int nb, int* sizes) {
   sizes[1] = nb - best;
 }
 
-int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream) {
-  JIMM_TRY(check_ready(m, B));
-  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
-  if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host on a dual-tower model"); return JIMM_EINVAL; }
-  JIMM_TRY(set_device(m));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
+// Host-buffer vision forward.  pre == nullptr: img_host holds NHWC images of in_dtype at the model's resolution.  pre != nullptr:
+// img_host holds raw uint8 RGB frames [B,Hin,Win,3]; each slice is copied as bytes (4x fewer than fp32 pixels), run through the image
+// front-end on the compute stream (resize / crop / rescale / normalise into the tower's operand dtype) and then through the tower.
+static int vit_forward_host_impl(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, cudaStream_t s,
+                                 jimm_preproc_t* pre, int Hin, int Win) {
   JIMM_TRY(ensure_copy_stream(m));
   const size_t img_elems = static_cast<size_t>(m->vis.img) * m->vis.img * m->vis.C;
-  const size_t img_bytes = img_elems * dtype_size(in_dtype);
+  const size_t src_bytes = pre ? static_cast<size_t>(Hin) * Win * 3 : img_elems * dtype_size(in_dtype);  // per image, on the host
+  const int tower_dtype = pre ? (m->cdt == DT_TF32 ? JIMM_F32 : m->cdt) : in_dtype;
   const int od = vision_out_dim(m);
+  const int kind = pre ? 1 : 0;
+  if (pre) {
+    const size_t need = static_cast<size_t>(m->max_batch) * src_bytes;
+    if (need > m->ws.in_u8_bytes) {  // first call (or larger frames): grow the byte staging buffer
+      JIMM_CUDA_CHECK(cudaDeviceSynchronize());
+      if (m->ws.in_u8) cudaFree(m->ws.in_u8);
+      m->ws.in_u8 = nullptr; m->ws.in_u8_bytes = 0;
+      JIMM_CUDA_CHECK(cudaMalloc(&m->ws.in_u8, need));
+      m->ws.in_u8_bytes = need;
+      m->host_chain = false;
+    }
+  }
   // Sliced pipeline per super-chunk of <= max_batch images: slice i+1 is copied on the side stream while slice i is in the
   // tower, and the next super-chunk's first copy overlaps this one's last forward.  The slices partition the staging buffer
-  // (max_batch fp32 images), one event pair each; one D2H of the super-chunk's result at its end.
+  // (max_batch images), one event pair each; one D2H of the super-chunk's result at its end.
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
     int sizes[jimm_model::kHostSlices];
     host_slices(m, nb, sizes);
-    bool same_layout = m->host_chain && m->host_chain_stream == s;
+    bool same_layout = m->host_chain && m->host_chain_stream == s && m->host_chain_kind == kind;
     for (int i = 0; i < jimm_model::kHostSlices; ++i) same_layout = same_layout && sizes[i] == m->host_chain_sizes[i];
     if (!same_layout) {
       // earlier work on the caller's stream may still read the staging buffer in another layout: order the copies after all of it
@@ -1011,19 +1027,24 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
       }
       m->host_chain = true;
       m->host_chain_stream = s;
+      m->host_chain_kind = kind;
     }
     int off = 0;
     for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
       const int n = sizes[slot];
       if (n <= 0) continue;
-      uint8_t* dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
+      uint8_t* img_dst = static_cast<uint8_t*>(m->ws.in_img) + static_cast<size_t>(off) * img_elems * sizeof(float);
+      uint8_t* copy_dst = pre ? m->ws.in_u8 + static_cast<size_t>(off) * src_bytes : img_dst;
       float* out_d = m->ws.out_dev + static_cast<size_t>(off) * od;
       if (m->slot_recorded[slot]) JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_consumed[slot], 0));
-      JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, static_cast<const uint8_t*>(img_host) + static_cast<size_t>(b0 + off) * img_bytes, n * img_bytes,
+      JIMM_CUDA_CHECK(cudaMemcpyAsync(copy_dst, static_cast<const uint8_t*>(img_host) + static_cast<size_t>(b0 + off) * src_bytes, n * src_bytes,
                                       cudaMemcpyHostToDevice, m->copy_stream));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
       JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
-      JIMM_TRY(exec_vision(m, dst, in_dtype, n, out_d, s));
+      if (pre) {
+        if (int rc = jimm_preproc_run(pre, copy_dst, n, Hin, Win, img_dst, tower_dtype, s)) return rc;
+      }
+      JIMM_TRY(exec_vision(m, img_dst, tower_dtype, n, out_d, s));
       JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       m->slot_recorded[slot] = true;
       off += n;
@@ -1032,6 +1053,29 @@ int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, i
                                     cudaMemcpyDeviceToHost, s));
   }
   return 0;
+}
+
+int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host on a dual-tower model"); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  return vit_forward_host_impl(m, img_host, in_dtype, B, out_host, static_cast<cudaStream_t>(stream), nullptr, 0, 0);
+}
+
+int jimm_vit_forward_host_u8(jimm_model_t* m, jimm_preproc_t* pre, const uint8_t* img_host, int B, int H, int W, float* out_host, void* stream) {
+  JIMM_TRY(check_ready(m, B));
+  if (!pre || !img_host || !out_host) { set_last_error("jimm_vit_forward_host_u8: null argument"); return JIMM_EINVAL; }
+  if (m->cfg.kind != JIMM_VIT && m->cfg.kind != JIMM_TOWER) { set_last_error("jimm_vit_forward_host_u8 on a dual-tower model"); return JIMM_EINVAL; }
+  if (m->vis.C != 3) { set_last_error("the image front-end produces 3-channel images; the model takes %d", m->vis.C); return JIMM_EINVAL; }
+  int oh = 0, ow = 0;
+  if (int rc = jimm_preproc_output_size(pre, H, W, &oh, &ow)) return rc;
+  if (oh != m->vis.img || ow != m->vis.img) {
+    set_last_error("front-end output %dx%d for %dx%d frames does not match the model's %dx%d input", oh, ow, H, W, m->vis.img, m->vis.img);
+    return JIMM_EINVAL;
+  }
+  JIMM_TRY(set_device(m));
+  return vit_forward_host_impl(m, img_host, JIMM_F32, B, out_host, static_cast<cudaStream_t>(stream), pre, H, W);
 }
 
 int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int Bi, const int32_t* ids_host, int Bt, int T,

@@ -29,9 +29,11 @@ OPENAI_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 OPENAI_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
-def _size_fields(size) -> dict:
+def _size_fields(size, default_to_square: bool = True) -> dict:
+    """HF `get_size_dict`: a legacy integer size is square for ViTImageProcessor / SiglipImageProcessor (default_to_square=True) and the
+    shortest edge for CLIPImageProcessor (default_to_square=False)."""
     if isinstance(size, int):
-        return {"shortest_edge": size}
+        return {"height": size, "width": size} if default_to_square else {"shortest_edge": size}
     if isinstance(size, (tuple, list)):
         return {"height": int(size[0]), "width": int(size[1])}
     if isinstance(size, dict):
@@ -50,7 +52,7 @@ class ImagePreprocessor:
     def __init__(self, size=None, crop_size=None, resample: int = BILINEAR, do_center_crop: Optional[bool] = None,
                  rescale_factor: float = 1 / 255, image_mean: Sequence[float] = (0.5, 0.5, 0.5),
                  image_std: Sequence[float] = (0.5, 0.5, 0.5), do_resize: bool = True, do_rescale: bool = True,
-                 do_normalize: bool = True, device: Optional[int] = None, **unused):
+                 do_normalize: bool = True, device: Optional[int] = None, default_to_square: bool = True, **unused):
         if not (do_resize and do_rescale and do_normalize):
             raise ValueError("the GPU front-end implements the full resize -> rescale -> normalize pipeline of the reference's examples")
         if int(resample) not in (BILINEAR, BICUBIC):
@@ -59,7 +61,7 @@ class ImagePreprocessor:
             raise ValueError("mean must have 3 elements if it is an iterable")
         if not all(image_std):
             raise ValueError("std evaluated to zero, leading to division by zero.")
-        f = _size_fields(size if size is not None else {"height": 224, "width": 224})
+        f = _size_fields(size if size is not None else {"height": 224, "width": 224}, default_to_square)
         cfg = _lib.PreprocConfig()
         cfg.height, cfg.width, cfg.shortest_edge = f.get("height", 0), f.get("width", 0), f.get("shortest_edge", 0)
         if do_center_crop is None:
@@ -106,6 +108,8 @@ class ImagePreprocessor:
         keys = ("size", "crop_size", "resample", "do_center_crop", "rescale_factor", "image_mean", "image_std", "do_resize",
                 "do_rescale", "do_normalize")
         args = {k: c[k] for k in keys if k in c and c[k] is not None}
+        # integer `size`: CLIPImageProcessor reads it as the shortest edge, ViT / SigLIP processors as a square
+        args["default_to_square"] = "clip" not in str(c.get("image_processor_type", "")).lower()
         args.update(kw)
         return cls(**args)
 

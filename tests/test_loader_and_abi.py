@@ -194,7 +194,8 @@ def test_front_end_and_epilogue_fail_loudly_without_gpu():
         ImagePreprocessor(size={"height": 8, "width": 8}, image_std=(0.5, 0.0, 0.5))
     with pytest.raises(ValueError):
         ImagePreprocessor(size={"longest_edge": 8})
-    assert _size_fields(224) == {"shortest_edge": 224}
+    assert _size_fields(224) == {"height": 224, "width": 224}  # ViT / SigLIP processors: legacy integer size is square
+    assert _size_fields(224, default_to_square=False) == {"shortest_edge": 224}  # CLIPImageProcessor
     assert _size_fields({"height": 3, "width": 5}) == {"height": 3, "width": 5}
     assert _size_fields((7, 9)) == {"height": 7, "width": 9}
 

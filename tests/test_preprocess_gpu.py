@@ -116,3 +116,58 @@ def test_front_end_feeds_the_tower(lib):
     assert torch.equal(out.argmax(-1).cpu(), ref.argmax(-1))
     # fp32 front-end output into the same tower gives the same bits: patchify rounds fp32 -> fp16 the same way
     assert torch.equal(m(proc(imgs, dtype=torch.float32)), out)
+
+
+def test_uint8_frames_through_the_model():
+    """Raw uint8 frames into the model (examples/vit_inference.py:27-58 end to end): host frames cross PCIe as bytes and go through the
+    front-end + tower inside jimm_vit_forward_host_u8's sliced pipeline; results equal front-end-then-model bit for bit, for host and
+    device frames, small (graph-replayed) and sliced (>= 128) batches, and the asynchronous dispatch."""
+    from jimm_b200.models import VisionTransformer
+    from jimm_b200.preprocess import ImagePreprocessor
+
+    torch.manual_seed(0)
+    m = VisionTransformer(num_classes=12, img_size=32, patch_size=8, num_layers=2, num_heads=2, mlp_dim=256, hidden_size=128,
+                          dtype=torch.float16).eval().set_max_batch(160)
+    proc = ImagePreprocessor.vit(32)
+    frames = torch.randint(0, 256, (150, 48, 64, 3), dtype=torch.uint8)
+    with pytest.raises(ValueError):
+        m(frames[:2])  # no front-end attached
+    m.set_preprocessor(proc)
+    ref = m(proc(frames.cuda(), dtype=torch.float16))
+    out_dev = m(frames.cuda())
+    assert torch.equal(out_dev, ref)
+    out_host = m(frames.pin_memory())
+    assert not out_host.is_cuda and torch.equal(out_host, ref.cpu())
+    for _ in range(3):  # small batch: staged + graph replay
+        assert torch.equal(m(frames[:5].contiguous()), ref[:5].cpu())
+    pend = [m.forward_async(frames.pin_memory()) for _ in range(3)]
+    for q in pend:
+        assert torch.equal(q.result(), ref.cpu())
+    # float inputs still work on the same model, and a frame size the front-end maps elsewhere is rejected
+    assert torch.equal(m(proc(frames[:4].cuda(), dtype=torch.float16).cpu()), ref[:4].cpu())
+    bad = ImagePreprocessor.vit(40)
+    m.set_preprocessor(bad)
+    with pytest.raises(ValueError):
+        m(frames[:2])
+
+
+def test_integer_size_is_square_for_vit_and_shortest_edge_for_clip(tmp_path):
+    """preprocessor_config.json with a legacy integer `size`: ViTImageProcessor / SiglipImageProcessor read it as a square
+    (default_to_square=True), CLIPImageProcessor as the shortest edge."""
+    import json
+
+    from jimm_b200.preprocess import ImagePreprocessor
+
+    (tmp_path / "vit").mkdir()
+    (tmp_path / "clip").mkdir()
+    json.dump({"image_processor_type": "ViTImageProcessor", "size": 32, "resample": 2, "image_mean": [0.5] * 3, "image_std": [0.5] * 3},
+              open(tmp_path / "vit" / "preprocessor_config.json", "w"))
+    json.dump({"image_processor_type": "CLIPImageProcessor", "size": 32, "crop_size": 32, "resample": 3, "image_mean": [0.5] * 3,
+               "image_std": [0.5] * 3}, open(tmp_path / "clip" / "preprocessor_config.json", "w"))
+    v = ImagePreprocessor.from_pretrained(str(tmp_path / "vit"))
+    c = ImagePreprocessor.from_pretrained(str(tmp_path / "clip"))
+    assert v.output_size(48, 64) == (32, 32)
+    assert c.output_size(48, 64) == (32, 32)  # shortest edge 32 -> 32x43, centre crop 32x32
+    x = torch.randint(0, 256, (2, 48, 64, 3), dtype=torch.uint8)
+    sq = ImagePreprocessor(size={"height": 32, "width": 32}, resample=2)
+    assert torch.equal(v(x), sq(x))
