@@ -14,6 +14,13 @@ ViT-B/16 @224, batch 256 per GPU, fp16 tensor-core operands (fp32 accumulate / r
   roofline: the dominant kernel (tcgen05 GEMM) timed live with CUDA events around every launch of the timed steps.
   cpu_baseline: the CPU oracle (torch fp32, jimm semantics -- the stand-in for the reference's JAX-CPU path, which cannot
            be installed here) on a bounded sample, rank 0 / N=1 only.
+  extra_workloads (N=1): north_star's second headline (SigLIP-B/16 @256) and BASELINE configs[2] (ViT-L/16 @384 MAP, bf16), a few steps
+           each: value, e2e and the live GEMM roofline, so that they are driver-measured too.
+  collective (N>1): after the ViT leg every rank runs the dual-tower path the batch-sharded reference resolves with an all-gather
+           (models/clip.py:183-187 under P("batch") inputs, examples/clip_inference.py:41-44): CLIP-B/32 at N<=4 (BASELINE configs[3] at N=4),
+           SigLIP2-L/16 @512 at N=8 (configs[4]).  Reports pairs/s (device and e2e), the fused normalise + NVLink peer-store + logits kernel
+           timed alone with CUDA events, bytes per peer, achieved NVLink GB/s against the measured 770 GB/s, and whether the sharded
+           logits are bit-identical to the single-GPU head on the gathered embeddings (checked outside the timed region).
 --impl reference times that CPU path alone, on the same metric / config (see the tier's reference-arm contract).
 """
 
@@ -126,6 +133,19 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+def synthetic_tokens(B: int, T: int, V: int, kind: str, seed: int):
+    """SURVEY.md 8(d): ids uniform in [1, V-2]; CLIP rows get one EOT = V-1 at a random position >= 1 (argmax pooling, models/clip.py:164);
+    SigLIP rows are full length (last-token pooling, models/siglip.py:151)."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(1, V - 1, (B, T), generator=g, dtype=torch.int64)
+    if kind == "clip":
+        pos = torch.randint(1, T, (B,), generator=g)
+        ids[torch.arange(B), pos] = V - 1
+    return ids
+
+
 def build_model(workload: str, dtype_name: str):
     """Random-init weights of the named architecture (no network for checkpoints): the reference's init distributions."""
     import torch
@@ -152,8 +172,7 @@ def build_model(workload: str, dtype_name: str):
 
 
 def cpu_threads() -> int:
-    """Threads for the CPU arm: every core this process may use (affinity mask and cgroup CPU quota honoured), capped at 32 --
-    torch's intra-op pool stops scaling, then regresses, beyond that for this model size; JIMM_CPU_THREADS overrides."""
+    """Threads for the CPU arm: every core this process may use (affinity mask and cgroup CPU quota honoured); JIMM_CPU_THREADS overrides."""
     env = os.environ.get("JIMM_CPU_THREADS")
     if env:
         return max(1, int(env))
@@ -168,7 +187,7 @@ def cpu_threads() -> int:
             n = min(n, max(1, int(int(quota) / int(period))))
     except Exception:
         pass
-    return max(1, min(n, 32))
+    return max(1, n)
 
 
 def oracle_step_fn(workload: str, B: int):
@@ -245,6 +264,194 @@ def run_reference(args):
     return 0
 
 
+def gemm_roofline(lib, native, step_dev, steps, ms_step):
+    """The dominant kernel (tcgen05 GEMM) timed live: CUDA events on the launch stream around every launch of `steps` steps."""
+    from jimm_b200 import _lib
+
+    _lib.check(lib.jimm_profile_begin(native.handle))
+    for _ in range(steps):
+        step_dev()
+    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
+    _lib.check(lib.jimm_profile_end(native.handle, C.byref(g_ms), C.byref(g_fl), C.byref(g_n)))
+    peak_tf, _, peak_src = peaks()
+    achieved = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src, "launches": g_n.value,
+            "avg_launch_ms": g_ms.value / max(g_n.value, 1), "gemm_share_of_step": g_ms.value / steps / ms_step}
+
+
+class Bench:
+    """One workload on this rank's GPU: model, synthetic inputs (device-resident, pinned fp32 host, pinned uint8 host) and timers."""
+
+    def __init__(self, workload, batch, rank, world, local, lib):
+        import torch
+
+        from jimm_b200 import dist as jd
+
+        self.torch, self.jd = torch, jd
+        self.workload, self.rank, self.world, self.lib = workload, rank, world, lib
+        self.dev = torch.device("cuda", local)
+        self.desc, B, self.dtype_name = WORKLOADS[workload]
+        self.B = batch or B
+        self.model, self.img_size, self.text = build_model(workload, self.dtype_name)
+        self.model.set_max_batch(self.B)
+        self.dual = self.text is not None
+        g = torch.Generator().manual_seed(1234 + rank)
+        self.img_host = torch.randn(self.B, self.img_size, self.img_size, 3, generator=g, dtype=torch.float32).pin_memory()
+        self.img_dev = self.img_host.to(self.dev)
+        self.ids_host = self.ids_dev = None
+        if self.dual:
+            self.ids_host = synthetic_tokens(self.B, self.text[0], self.text[1], self.text[2], seed=4321 + rank).to(torch.int32).pin_memory()
+            self.ids_dev = self.ids_host.to(self.dev)
+            self.step_dev = lambda: self.model(self.img_dev, self.ids_dev)
+            self.step_host = lambda: self.model(self.img_host, self.ids_host)
+            self.step_host_u8 = None
+        else:
+            self.step_dev = lambda: self.model(self.img_dev)
+            self.step_host = lambda: self.model(self.img_host)
+            # raw frames: what examples/vit_inference.py:27-37 feeds its (host) image processor; here they cross PCIe as bytes and the
+            # front-end (resize to the model size = identity window, rescale, normalise) runs on the GPU ahead of the tower
+            from jimm_b200.preprocess import ImagePreprocessor
+
+            self.u8_host = torch.randint(0, 256, (self.B, self.img_size, self.img_size, 3), generator=g, dtype=torch.uint8).pin_memory()
+            self.model.set_preprocessor(ImagePreprocessor.vit(self.img_size))
+            self.step_host_u8 = lambda: self.model(self.u8_host)
+
+    def barrier(self):
+        if self.world > 1:
+            self.torch.distributed.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        return self.jd.max_over_ranks(e0.elapsed_time(e1)), out
+
+    def rate(self, ms_total, steps):
+        return self.world * self.B * steps / (ms_total * 1e-3)
+
+    def e2e(self, steps, pipelined=True):
+        """Host buffers through the public API: H2D + forward + D2H inside the timed region, synchronised every step."""
+        out = {}
+        for _ in range(2):
+            self.step_host()
+        ms, out_h = self.timed(self.step_host, steps)
+        f32 = {"value": self.rate(ms, steps), "ms_per_step": ms / steps,
+               "h2d_bytes_per_step": self.img_host.numel() * 4 + (self.ids_host.numel() * 4 if self.dual else 0)}
+        d2h = out_h.numel() * 4
+        if self.step_host_u8 is None:
+            out = {"value": f32["value"], "unit": "images/sec", "h2d_bytes_per_step": f32["h2d_bytes_per_step"], "d2h_bytes_per_step": d2h,
+                   "ms_per_step": f32["ms_per_step"], "input": "pinned fp32 NHWC pixel values + int32 token ids", "sync": "every step"}
+        else:
+            for _ in range(2):
+                self.step_host_u8()
+            ms8, _ = self.timed(self.step_host_u8, steps)
+            out = {"value": self.rate(ms8, steps), "unit": "images/sec", "h2d_bytes_per_step": self.u8_host.numel(), "d2h_bytes_per_step": d2h,
+                   "ms_per_step": ms8 / steps, "sync": "every step",
+                   "input": "pinned uint8 RGB frames; GPU image front-end (jimm_preproc_run) + tower inside the timed region",
+                   "fp32_input": f32}
+            if pipelined and hasattr(self.model, "forward_async"):
+                # the same loop with asynchronous dispatch, two calls in flight (every step still copies its inputs in and its result out)
+                state = {"pending": None}
+
+                def step_async():
+                    nxt = self.model.forward_async(self.u8_host)
+                    res = state["pending"].result() if state["pending"] is not None else None
+                    state["pending"] = nxt
+                    return res
+
+                for _ in range(2):
+                    step_async()
+                ms_pipe, _ = self.timed(step_async, steps)
+                state["pending"].result()
+                out["pipelined_depth2_value"] = self.rate(ms_pipe, steps)
+        return out
+
+
+def collective_leg(args, rank, world, local, lib):
+    """N > 1: the dual-tower path with its one exchange step (embedding all-gather fused into the logits kernel over NVLink peer memory)."""
+    import torch
+    import torch.distributed as dist
+
+    wl = "siglip2_l16_512" if world >= 8 else "clip_b32"
+    steps = max(2, min(args.steps, 3 if wl == "siglip2_l16_512" else 10))
+    bw = Bench(wl, 0, rank, world, local, lib)
+    m, B = bw.model, bw.B
+    m.set_comm("peer")
+    for _ in range(3):
+        bw.step_dev()
+    torch.cuda.synchronize(bw.dev)
+    ms, out = bw.timed(bw.step_dev, steps)
+    for _ in range(2):
+        bw.step_host()
+    ms_h, _ = bw.timed(bw.step_host, steps)
+    n = m.native(B, require=True)
+    # ---- the collective kernel alone: encoder outputs resident, CUDA events around `reps` back-to-back calls (every call carries its
+    #      own cross-GPU flag barrier, so the ranks run it in lock-step), max over ranks
+    ie, te = n.vision(bw.img_dev, encode=True), n.text(bw.ids_dev)
+    reps = 50
+    for _ in range(5):
+        lg = n.comm_logits(ie, te)
+    ms_k, lg = bw.timed(lambda: n.comm_logits(ie, te), reps)
+    # NCCL baseline of the same exchange (normalise + all_gather_into_tensor + local logits), for context
+    m.set_comm("nccl")
+    for _ in range(5):
+        m._distributed_logits(n, ie, te, B)
+    ms_n, lg_nccl = bw.timed(lambda: m._distributed_logits(n, ie, te, B), reps)
+    m.set_comm("peer")
+    # ---- bit-identity with the single-GPU head (outside the timed region): gather the raw embeddings with NCCL, run the one-GPU head
+    E = ie.shape[1]
+    ie_all, te_all = torch.empty((world * B, E), device=bw.dev), torch.empty((world * B, E), device=bw.dev)
+    dist.all_gather_into_tensor(ie_all, ie.contiguous())
+    dist.all_gather_into_tensor(te_all, te.contiguous())
+    # (the single-GPU head = l2_normalize + logits kernels of jimm_contrastive_logits, called through their per-kernel entry points because
+    # the gathered text batch exceeds this handle's max_batch)
+    def vp(t):
+        return C.c_void_p(t.data_ptr())
+
+    st = C.c_void_p(torch.cuda.current_stream(bw.dev).cuda_stream)
+    ie_rows = ie_all[rank * B:(rank + 1) * B].contiguous()
+    ni, nt = torch.empty_like(ie_rows), torch.empty_like(te_all)
+    _lib_check = __import__("jimm_b200._lib", fromlist=["check"]).check
+    _lib_check(lib.jimm_k_l2_normalize(vp(ie_rows), vp(ni), E, B, E, st))
+    _lib_check(lib.jimm_k_l2_normalize(vp(te_all), vp(nt), E, world * B, E, st))
+    fp = m.flat_params()
+    scale = fp["logit_scale"].to(bw.dev).reshape(1).contiguous()
+    bias = fp["logit_bias"].to(bw.dev).reshape(1).contiguous() if "logit_bias" in fp else None
+    single = torch.empty((B, world * B), dtype=torch.float32, device=bw.dev)
+    _lib_check(lib.jimm_k_logits(vp(ni), vp(nt), vp(scale), vp(bias) if bias is not None else None, vp(single), B, world * B, E, world * B, st))
+    same = torch.tensor([int(torch.equal(single, lg))], device=bw.dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    nccl_diff = bw.jd.max_over_ranks(float((lg_nccl - lg).abs().max()))
+    bytes_per_peer = B * 2 * E * 4
+    us = ms_k / reps * 1e3
+    egress = bytes_per_peer * (world - 1)
+    return {
+        "workload": WORKLOADS[wl][0] + f" x {world} GPUs = global batch {world * B}", "kernel": "comm_logits_kernel (csrc/comm.cu)",
+        "reference_step": "the all-gather XLA inserts for image_features @ text_features.T under batch-sharded inputs "
+                          "(models/clip.py:183-187, models/siglip.py:169-173, examples/clip_inference.py:41-44)",
+        "value": bw.rate(ms, steps), "unit": "pairs/sec", "ms_per_step": ms / steps, "steps": steps,
+        "e2e": {"value": bw.rate(ms_h, steps), "unit": "pairs/sec", "ms_per_step": ms_h / steps,
+                "h2d_bytes_per_step": bw.img_host.numel() * 4 + bw.ids_host.numel() * 4, "d2h_bytes_per_step": B * world * B * 4},
+        "us_per_call": us, "calls_timed": reps, "bytes_sent_per_peer": bytes_per_peer, "peers": world - 1,
+        "nvlink_egress_gbs": egress / (us * 1e-6) / 1e9, "nvlink_peak_gbs": 770.0, "nvlink_frac": egress / (us * 1e-6) / 1e9 / 770.0,
+        "note": "latency-bound by construction: %.2f MiB per peer is %.1f us of NVLink time at 770 GB/s; the rest is normalise + flag barrier + "
+                "the [B_local, B_global] logits tile" % (bytes_per_peer / 2**20, bytes_per_peer / 770e9 * 1e6),
+        "nccl_allgather_us_per_call": ms_n / reps * 1e3, "max_abs_diff_vs_nccl_path": nccl_diff,
+        "bit_identical_to_single_gpu": bool(same.item()), "collective_share_of_step": us * 1e-3 / (ms / steps),
+    }
+
+
 def run_ours(args):
     import torch
 
@@ -255,45 +462,10 @@ def run_ours(args):
     if world != args.gpus and world > 1:
         args.gpus = world
     torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
     build.build()
     lib = _lib.load()
-    desc, B, dtype_name = WORKLOADS[args.workload]
-    if args.batch:
-        B = args.batch
-    model, img_size, text = build_model(args.workload, dtype_name)
-    model.set_max_batch(B)
-    dual = text is not None
-
-    g = torch.Generator().manual_seed(1234 + rank)
-    img_host = torch.randn(B, img_size, img_size, 3, generator=g, dtype=torch.float32).pin_memory()
-    img_dev = img_host.to(dev)
-    if dual:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import jimm_oracle as O
-
-        ids_host = O.synthetic_tokens(B, text[0], text[1], text[2], seed=4321 + rank).to(torch.int32).pin_memory()
-        ids_dev = ids_host.to(dev)
-        step_dev = lambda: model(img_dev, ids_dev)
-        step_host = lambda: model(img_host, ids_host)
-    else:
-        step_dev = lambda: model(img_dev)
-        step_host = lambda: model(img_host)
-
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize(dev)
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        return jd.max_over_ranks(e0.elapsed_time(e1)), out
+    bw = Bench(args.workload, args.batch, rank, world, local, lib)
+    B, dev = bw.B, bw.dev
 
     # ---- warm-up (also builds the native handle); the clock sampler is started first so that nvidia-smi is already streaming
     #      when the timed region begins (its start-up can take longer than a short timed region) ----
@@ -301,14 +473,14 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step_dev()
+        bw.step_dev()
     torch.cuda.synchronize(dev)
-    native = model.native(B)
+    native = bw.model.native(B)
 
     # ---- value: device-resident inputs ----
     l0 = lib.jimm_launch_count()
     sampler.mark_begin()
-    ms_total, out = timed(step_dev, args.steps)
+    ms_total, out = bw.timed(bw.step_dev, args.steps)
     sampler.mark_end()
     launches = lib.jimm_launch_count() - l0
     clocks = None
@@ -317,51 +489,42 @@ def run_ours(args):
             # the region was shorter than the sampling period: keep the same load running (untimed) until a sample lands
             t_wait = time.time()
             while len([1 for t, _ in sampler.rows if t >= sampler.t1]) < 2 and time.time() - t_wait < 3.0:
-                step_dev()
+                bw.step_dev()
                 torch.cuda.synchronize(dev)
         clocks = sampler.stop()
     ms_step = ms_total / args.steps
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = bw.rate(ms_total, args.steps)
+    roofline = gemm_roofline(lib, native, bw.step_dev, args.steps, ms_step)
+    e2e = bw.e2e(args.steps)
+    peak_tf = roofline["peak"]
 
-    # ---- roofline: tcgen05 GEMM launches of the same steps, bracketed by events on the launch stream ----
-    _lib.check(lib.jimm_profile_begin(native.handle))
-    for _ in range(args.steps):
-        step_dev()
-    g_ms, g_fl, g_n = C.c_double(), C.c_double(), C.c_longlong()
-    _lib.check(lib.jimm_profile_end(native.handle, C.byref(g_ms), C.byref(g_fl), C.byref(g_n)))
-    peak_tf, peak_bw, peak_src = peaks()
-    achieved = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf, "traffic": traffic, "peak_source": peak_src, "launches": g_n.value,
-                "avg_launch_ms": g_ms.value / max(g_n.value, 1), "gemm_share_of_step": g_ms.value / args.steps / ms_step}
+    # ---- N = 1 extras: the other headline workloads, a few steps each ----
+    extras = None
+    if world == 1 and not args.no_extras and args.workload == "vit_b16":
+        extras = {}
+        for wl, steps in (("siglip_b16", 8), ("vit_l16_map", 5)):
+            del bw  # free the previous model's workspace before the next one is built
+            torch.cuda.empty_cache()
+            bw = Bench(wl, 0, rank, world, local, lib)
+            for _ in range(3):
+                bw.step_dev()
+            torch.cuda.synchronize(dev)
+            ms_x, _ = bw.timed(bw.step_dev, steps)
+            v = bw.rate(ms_x, steps)
+            rf = gemm_roofline(lib, bw.model.native(bw.B), bw.step_dev, steps, ms_x / steps)
+            ex = bw.e2e(steps, pipelined=False)
+            extras[wl] = {"workload": bw.desc, "value": v, "unit": "pairs/sec" if bw.dual else "images/sec", "ms_per_step": ms_x / steps, "steps": steps,
+                          "dtype": {"float16": "f16", "bfloat16": "bf16"}[bw.dtype_name], "gflop_per_unit": GFLOP_PER_IMG[wl],
+                          "model_tflops": v * GFLOP_PER_IMG[wl] / 1e3, "model_frac_of_peak": v * GFLOP_PER_IMG[wl] / 1e3 / peak_tf,
+                          "e2e": ex, "gemm_tflops": rf["achieved"], "gemm_frac": rf["frac"], "gemm_share_of_step": rf["gemm_share_of_step"]}
+        bw = None
 
-    # ---- e2e: host buffers through the public API (H2D + forward + D2H inside the timed region) ----
-    for _ in range(2):
-        step_host()
-    ms_e2e, out_h = timed(step_host, args.steps)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    # the same loop with asynchronous dispatch, two calls in flight (every step still copies its inputs in and its result out)
-    pipelined = None
-    if not dual and hasattr(model, "forward_async"):
-        state = {"pending": None}
-
-        def step_async():
-            nxt = model.forward_async(img_host)
-            out = state["pending"].result() if state["pending"] is not None else None
-            state["pending"] = nxt
-            return out
-
-        for _ in range(2):
-            step_async()
-        ms_pipe, _ = timed(step_async, args.steps)
-        state["pending"].result()
-        pipelined = world * B * args.steps / (ms_pipe * 1e-3)
-    h2d = img_host.numel() * 4 + (ids_host.numel() * 4 if dual else 0)
-    d2h = out_h.numel() * 4
+    # ---- N > 1: the dual-tower leg with the fused NVLink exchange ----
+    collective = None
+    if world > 1 and not args.no_collective:
+        bw = None
+        torch.cuda.empty_cache()
+        collective = collective_leg(args, rank, world, local, lib)
 
     # ---- CPU baseline (rank 0, N=1 only; bounded sample) ----
     cpu = None
@@ -376,6 +539,7 @@ def run_ours(args):
 
     if rank == 0:
         gflop = GFLOP_PER_IMG[args.workload]
+        desc, _, dtype_name = WORKLOADS[args.workload]
         line = {
             "metric": "images/sec", "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -384,10 +548,12 @@ def run_ours(args):
                        "l2_policy": "inputs_larger_than_L2 (154 MB fp32 images; >1 GB of activations streamed per step)",
                        "gflop_per_image": gflop},
             "model_tflops": value * gflop / 1e3, "model_frac_of_peak": value * gflop / 1e3 / (peak_tf * world),
-            "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "sync": "every step (value above)", "pipelined_depth2_value": pipelined},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if extras is not None:
+            line["extra_workloads"] = extras
+        if collective is not None:
+            line["collective"] = collective
         print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.barrier()
@@ -407,6 +573,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=0, help="0 = size the CPU sample for ~12 s")
     ap.add_argument("--cpu-batch-fixed", action="store_true", help="reference arm: use --cpu-batch instead of sizing it from a probe")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the SigLIP-B/16@256 and ViT-L/16@384 legs")
+    ap.add_argument("--no-collective", action="store_true", help="N>1: skip the dual-tower leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -116,6 +116,10 @@ JIMM_API int jimm_comm_connect(jimm_model_t* m, const unsigned char* handles /*[
  * logits_local fp32 [B_local, world*B_local] = exp(scale) * I_local . T_all^T (+ bias).  No host synchronisation. */
 JIMM_API int jimm_comm_contrastive_logits(jimm_model_t* m, const float* img_e, const float* txt_e, int B_local, float* logits_local,
                                  void* stream);
+/* The device-side wait for the peers is bounded (JIMM_COMM_TIMEOUT_MS, default 10 s) and every rank must pass the same B_local: a
+ * missing or mismatched peer yields NaN logits and a sticky error, returned here (after the stream has been synchronised) and by the
+ * next jimm_comm_contrastive_logits call. */
+JIMM_API int jimm_comm_status(jimm_model_t* m);
 /* Device pointer to this rank's gathered, normalised [world*B_local, 2E] buffer (valid after the call above). */
 JIMM_API int jimm_comm_gathered(jimm_model_t* m, float** gathered, int* row_stride);
 

@@ -69,6 +69,7 @@ SIGNATURES = {
     "jimm_comm_init": (_i, [_vp, _i, _i, _i, C.c_char_p]),
     "jimm_comm_connect": (_i, [_vp, C.c_char_p]),
     "jimm_comm_contrastive_logits": (_i, [_vp, _fp, _fp, _i, _fp, _vp]),
+    "jimm_comm_status": (_i, [_vp]),
     "jimm_comm_gathered": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i)]),
     "jimm_profile_begin": (_i, [_vp]),
     "jimm_profile_end": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),

@@ -19,12 +19,16 @@ struct CommState {
   unsigned int* counter = nullptr;  // local CTA-completion ticket counter
   unsigned long long epoch = 0;
   int grid = 0;
+  unsigned int* status_host = nullptr;  // host-mapped error word written by the kernel (0 = fine)
+  unsigned int* status_dev = nullptr;
+  unsigned long long timeout_ns = 0;    // bound of the device-side wait for the peers
 };
 
 int comm_init(CommState* c, int rank, int world, int max_rows, int E, unsigned char* handle_out);
 int comm_connect(CommState* c, const unsigned char* handles);
 int comm_contrastive_logits(CommState* c, const float* img_e, const float* txt_e, int B_local, const float* logit_scale,
                             const float* logit_bias, float* logits_local, cudaStream_t stream);
+int comm_status(CommState* c);
 void comm_destroy(CommState* c);
 
 }  // namespace jimm

@@ -1145,6 +1145,10 @@ int jimm_comm_contrastive_logits(jimm_model_t* m, const float* img_e, const floa
   JIMM_TRY(set_device(m));
   return comm_contrastive_logits(&m->comm, img_e, txt_e, B_local, m->logit_scale, m->logit_bias, logits_local, static_cast<cudaStream_t>(stream));
 }
+int jimm_comm_status(jimm_model_t* m) {
+  if (!m) { set_last_error("null model"); return JIMM_EINVAL; }
+  return comm_status(&m->comm);
+}
 int jimm_comm_gathered(jimm_model_t* m, float** gathered, int* row_stride) {
   if (!m || !m->comm.ready) { set_last_error("comm not initialised"); return JIMM_ESTATE; }
   if (gathered) *gathered = m->comm.local_buf;

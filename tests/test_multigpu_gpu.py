@@ -85,5 +85,10 @@ def test_sharded_contrastive_head(kind):
     for p in procs:
         p.join(120)
         assert p.exitcode == 0
+    from gpu_util import record_parity
+
     for rank, errs in res:
-        assert all(e < 2e-3 for e in errs), (rank, errs)  # fp16 towers x exp(logit_scale); the exact check is vs the single-GPU head
+        # the sharded head is asserted BIT-IDENTICAL to the single-GPU head inside the workers; against the fp32 oracle the logits carry the
+        # fp16 towers' error amplified by exp(logit_scale) (tests/test_parity_gpu.py LOGITS_TOL), recorded here
+        record_parity(f"multi-GPU {kind} head, world {world}, rank {rank}", "logits row block", "float16", "fp32", 2e-3, max(errs))
+        assert all(e < 2e-3 for e in errs), (rank, errs)

@@ -19,6 +19,7 @@ TOL = 1e-3  # north_star: 1e-3 relative vs the fp32 path
 # bf16 operands (8-bit significand): the CUDA path keeps the residual stream / LN / softmax in fp32, the reference's own bf16 path
 # (flax dtype=bf16) rounds every layer output.  Both are compared with the fp32 oracle; the CUDA path must not be further from
 # fp32 than BF16_VS_FP32, and must stay within BF16_VS_SAME of the oracle run with the same operand rounding.
+LOGITS_TOL = 2e-3  # contrastive logits: the embedding error amplified by exp(logit_scale) (see test_config4_shape_clip_b32_reduced_depth)
 BF16_VS_SAME = 8e-3
 BF16_VS_FP32 = 1.5e-2
 
@@ -245,10 +246,16 @@ def test_config4_shape_clip_b32_reduced_depth():
     img, txt = O.synthetic_images(5, 224), O.synthetic_tokens(7, 77, 49408, "clip")
     with torch.no_grad():
         ref = O.clip_forward(p, cfg, img, txt)
+        ref_i, ref_t = O.clip_encode_image(p, cfg, img), O.clip_encode_text(p, cfg, txt)
     m = _set(CLIP(224, 2, 768, 32, 77, 49408, 512, 8, 2, dtype=torch.float16), p)
+    case = "c4 shapes CLIP-B/32, 2+2 layers"
+    check_parity(case, "image_embeds", torch.float16, "fp32", m.encode_image(img.cuda()), ref_i, TOL)
+    check_parity(case, "text_embeds", torch.float16, "fp32", m.encode_text(txt.cuda()), ref_t, TOL)
     out = m(img.cuda(), txt.cuda())
     assert out.shape == (5, 7)
-    check_parity("c4 shapes CLIP-B/32, 2+2 layers", "logits", torch.float16, "fp32", out, ref, TOL)
+    # logits = exp(logit_scale) * cos(i, t): an error of e in the unit-norm embeddings becomes ~ exp(2.66) * e = 14 e on a logit whose
+    # maximum is a fraction of 14, so the tower's 1e-3 bar corresponds to a looser one on the logits; the achieved value is in PARITY.md
+    check_parity(case, "logits", torch.float16, "fp32", out, ref, LOGITS_TOL)
     assert torch.equal(out.argmax(-1).cpu(), ref.argmax(-1))
 
 
@@ -269,7 +276,7 @@ def test_config5_shape_siglip2_l16_512_reduced_depth():
     out = m(img.cuda(), txt.cuda())
     # logits = exp(logit_scale) * cos + bias: the embedding error (<1e-3 of max|emb|) is amplified by exp(2.3) ~ 10 against
     # max|logit| ~ |bias| + 10*|cos|; bound 2e-3, achieved value in PARITY.md
-    check_parity(case, "logits", torch.float16, "fp32", out, ref, 2e-3)
+    check_parity(case, "logits", torch.float16, "fp32", out, ref, LOGITS_TOL)
 
 
 @pytest.mark.parametrize("kind", ["clip", "siglip"])
@@ -512,7 +519,7 @@ def test_config5_full_depth_tf32_and_fp16(c5_full, dtype):
     check_parity(C5, "text_embeds", dtype, "fp32", emb_t, ref_t, TOL)
     out = m(img.cuda(), txt.cuda())
     assert out.shape == (1, 2)
-    check_parity(C5, "logits", dtype, "fp32", out, ref, 2e-3)  # exp(logit_scale) amplification, see the reduced-depth test
+    check_parity(C5, "logits", dtype, "fp32", out, ref, LOGITS_TOL)
 
 
 def test_config5_full_depth_bf16(c5_full):
@@ -554,7 +561,7 @@ def test_config4_full_depth_clip_b32():
         check_parity(case, "text_embeds", dtype, "fp32", m.encode_text(txt.cuda()), ref_t, TOL)
         out = m(img.cuda(), txt.cuda())
         assert out.shape == (6, 5)
-        check_parity(case, "logits", dtype, "fp32", out, ref, 2e-3)
+        check_parity(case, "logits", dtype, "fp32", out, ref, LOGITS_TOL)
         assert torch.equal(out.argmax(-1).cpu(), ref.argmax(-1))
 
 
@@ -577,4 +584,4 @@ def test_siglip_b16_256_full_depth():
         check_parity(case, "text_embeds", dtype, "fp32", m.encode_text(txt.cuda()), ref_t, TOL)
         out = m(img.cuda(), txt.cuda())
         assert out.shape == (4, 3)
-        check_parity(case, "logits", dtype, "fp32", out, ref, 2e-3)
+        check_parity(case, "logits", dtype, "fp32", out, ref, LOGITS_TOL)
