@@ -90,6 +90,11 @@ JIMM_API int jimm_encode_text(jimm_model_t* m, const int32_t* ids, int B, int T,
 /* L2-normalise + exp(logit_scale) * I . T^T (+ logit_bias) (models/clip.py:183-187, models/siglip.py:169-173).
  * img_e fp32 [Bi,E], txt_e fp32 [Bt,E] (un-normalised encoder outputs), logits fp32 [Bi,Bt] row stride Bt. */
 JIMM_API int jimm_contrastive_logits(jimm_model_t* m, const float* img_e, int Bi, const float* txt_e, int Bt, float* logits, void* stream);
+/* encode_image + encode_text of one CLIP / SigLIP call with the two (independent) towers running CONCURRENTLY: the text tower is forked onto
+ * a side stream and joined back into `stream`, so the idle SMs of one tower's GEMM tail rounds are filled by the other tower.
+ * img_e fp32 [Bi,E], txt_e fp32 [Bt,E] (un-normalised, as jimm_encode_image / jimm_encode_text return them). */
+JIMM_API int jimm_dual_encode(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* img_e, float* txt_e,
+                     void* stream);
 /* CLIP.__call__ / SigLIP.__call__ (models/clip.py:169-188, models/siglip.py:155-174) on one GPU. */
 JIMM_API int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* logits,
                       void* stream);

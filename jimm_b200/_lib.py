@@ -62,6 +62,7 @@ SIGNATURES = {
     "jimm_encode_image": (_i, [_vp, _vp, _i, _i, _fp, _vp]),
     "jimm_encode_text": (_i, [_vp, _ip, _i, _i, _fp, _vp]),
     "jimm_contrastive_logits": (_i, [_vp, _fp, _i, _fp, _i, _fp, _vp]),
+    "jimm_dual_encode": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _fp, _vp]),
     "jimm_dual_forward": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),
     "jimm_vit_forward_host": (_i, [_vp, _vp, _i, _i, _fp, _vp]),
     "jimm_dual_forward_host": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),

@@ -193,6 +193,16 @@ class NativeModel:
                 out = out.cpu()
         return out
 
+    def dual_encode(self, x: torch.Tensor, ids: torch.Tensor):
+        """encode_image + encode_text of device-resident inputs with the two towers running concurrently (jimm_dual_encode)."""
+        Bi, (Bt, T) = x.shape[0], ids.shape
+        with torch.cuda.device(self.device):
+            ie = torch.empty((Bi, self.vision_out), dtype=torch.float32, device=self.device)
+            te = torch.empty((Bt, self.text_out), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.jimm_dual_encode(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], Bi, C.c_void_p(ids.data_ptr()), Bt, T,
+                                                 C.c_void_p(ie.data_ptr()), C.c_void_p(te.data_ptr()), C.c_void_p(_stream_ptr(self.device))))
+        return ie, te
+
     def logits(self, img_e: torch.Tensor, txt_e: torch.Tensor) -> torch.Tensor:
         with torch.cuda.device(self.device):
             img_e = img_e.to(self.device, torch.float32).contiguous()

@@ -141,6 +141,17 @@ struct TextTower {
   GemmPlan p_head;
 };
 
+// The text tower has its own residual stream / activation buffers so that the two towers of CLIP / SigLIP can run CONCURRENTLY on two
+// streams (they are independent until the contrastive head): the tail rounds of one tower's persistent GEMMs and its small kernels are
+// filled by the other tower's CTAs instead of leaving SMs idle.
+struct TextWs {
+  float* x = nullptr;     // fp32 residual stream [Bmax*T, Dt]
+  void* h = nullptr;      // LN out / attention out
+  void* big = nullptr;    // qkv | mlp hidden
+  void* pooled = nullptr; // [Bmax, Dt]
+  int* idx = nullptr;     // [Bmax] EOT positions
+};
+
 struct Workspace {
   float* x = nullptr;     // fp32 residual stream [Tmax, Dmax]
   void* h = nullptr;      // LN out / attention out (compute dtype) [Tmax, Dmax]
@@ -179,6 +190,13 @@ struct jimm_model {
   float* logit_scale = nullptr;
   float* logit_bias = nullptr;
   Workspace ws;
+  TextWs wt;
+  // two-stream execution of the dual towers (JIMM_DUAL_STREAMS=0 disables): text tower on `text_stream`, forked from / joined to the
+  // caller's stream with events
+  bool dual_streams = true;
+  cudaStream_t text_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* graph_out_t = nullptr;  // text-tower twin of graph_out
   CommState comm;
   cudaStream_t copy_stream = nullptr;            // host path: H2D of chunk i+1 overlaps the forward of chunk i
   static constexpr int kHostSlices = 4;
@@ -380,9 +398,14 @@ static GemmEpilogue epi_residual(const LinearW& w, float* x, int ld, int mode) {
   return e;
 }
 
-static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax) {
+struct EncBufs {  // the activation buffers one encoder stack works in
+  float* x;
+  void* h;
+  void* big;
+};
+
+static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax, EncBufs ws) {
   const EncoderCfg& c = enc->c;
-  Workspace& ws = m->ws;
   const int act = c.act == JIMM_QUICK_GELU ? ACT_QUICK_GELU : ACT_GELU_TANH;
   for (BlockW& b : enc->blocks) {
     // QKV: h[T,D] x Wqkv[3D,D]^T + b -> qkv (16-bit) [T,3D]
@@ -400,9 +423,8 @@ static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax) {
 }
 
 // x: fp32 [B*S, D] residual stream in ws.x.  TransformerEncoder.__call__ x L (common/transformer.py:116-132,190-196).
-static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s) {
+static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s, EncBufs ws) {
   const EncoderCfg& c = enc->c;
-  Workspace& ws = m->ws;
   const int T = B * S;
   // Boustrophedon schedule: every kernel walks its rows / tiles / items in the direction opposite to its producer, so it
   // starts on the data written last -- the part of the 77-310 MB activation still resident in the 126 MB L2.
@@ -436,7 +458,7 @@ static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float
     if (v.pooling == JIMM_POOL_CLS) JIMM_TRY(cls_row_run(ws.x, v.cls, v.pos, B, S, D, s));
   }
   if (v.pre_norm) JIMM_TRY(layernorm_run(ws.x, D, 1, 0, nullptr, v.ln_pre.scale, v.ln_pre.bias, v.eps_outer, ws.x, DT_F32, D, B * S, D, s));
-  JIMM_TRY(run_encoder(m, &v.enc, B, S, s));
+  JIMM_TRY(run_encoder(m, &v.enc, B, S, s, EncBufs{ws.x, ws.h, ws.big}));
   if (v.pooling == JIMM_POOL_CLS) {
     // ln_post is per-row, only row 0 of each sample is consumed (common/vit.py:244-246)
     if (v.head.N > 0) {
@@ -468,9 +490,9 @@ static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float
 // CLIP.encode_text (models/clip.py:148-167) / SigLIP.encode_text (models/siglip.py:135-153).  out fp32 [B, Dt]
 static int run_text(jimm_model* m, const int32_t* ids, int B, int T, float* out, cudaStream_t s) {
   TextTower& t = m->txt;
-  Workspace& ws = m->ws;
+  TextWs& ws = m->wt;
   JIMM_TRY(embed_run(ids, t.table, t.pos, ws.x, B, T, t.D, t.V, s));
-  JIMM_TRY(run_encoder(m, &t.enc, B, T, s));
+  JIMM_TRY(run_encoder(m, &t.enc, B, T, s, EncBufs{ws.x, ws.h, ws.big}));
   if (t.pool == JIMM_TPOOL_EOT_ARGMAX) {
     JIMM_TRY(argmax_ids_run(ids, ws.idx, B, T, s));
     JIMM_TRY(layernorm_run(ws.x, t.D, T, 0, ws.idx, t.ln_final.scale, t.ln_final.bias, t.eps_outer, ws.pooled, m->cdt, t.D, B, t.D, s));
@@ -573,10 +595,10 @@ static int exec_vision(jimm_model* m, const void* img, int in_dtype, int n, floa
 }
 
 static int exec_text(jimm_model* m, const int32_t* ids, int n, int T, float* out, cudaStream_t s) {
-  if (n <= 0 || n > m->graph_max_batch || !m->graph_out) return run_text(m, ids, n, T, out, s);
+  if (n <= 0 || n > m->graph_max_batch || !m->graph_out_t) return run_text(m, ids, n, T, out, s);
   if (ids != m->ws.in_ids) JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids, static_cast<size_t>(n) * T * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
-  JIMM_TRY(run_graphed(m, std::make_tuple(1, n, T), s, [&](cudaStream_t cs) { return run_text(m, m->ws.in_ids, n, T, m->graph_out, cs); }));
-  JIMM_CUDA_CHECK(cudaMemcpyAsync(out, m->graph_out, static_cast<size_t>(n) * m->txt.D * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  JIMM_TRY(run_graphed(m, std::make_tuple(1, n, T), s, [&](cudaStream_t cs) { return run_text(m, m->ws.in_ids, n, T, m->graph_out_t, cs); }));
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(out, m->graph_out_t, static_cast<size_t>(n) * m->txt.D * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
@@ -635,6 +657,7 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   m->simt = env && strcmp(env, "simt") == 0;
   if ((env = getenv("JIMM_L2_ALTERNATE"))) m->l2_alternate = atoi(env) != 0;
   if ((env = getenv("JIMM_GRAPH_MAX_BATCH"))) m->graph_max_batch = atoi(env) > 0 ? atoi(env) : 0;
+  if ((env = getenv("JIMM_DUAL_STREAMS"))) m->dual_streams = atoi(env) != 0;
   if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env);
   if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env);
   *out = m;
@@ -769,12 +792,16 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   upd(Tv * 3 * D * 2);                   // qkv (16-bit)
   upd(Tv * static_cast<size_t>(c.v_mlp) * cs);  // MLP hidden
   if (v.pooling == JIMM_POOL_MAP) upd(Tv * 2 * D * 2);
-  if (dual) {
+  if (dual) {  // the text tower's own buffers (it runs concurrently with the vision tower)
     const size_t Tt = Bm * t.T;
-    if (Tt * t.D > x_elems) x_elems = Tt * t.D;
-    if (static_cast<size_t>(t.D) > Dmax) Dmax = t.D;
-    upd(Tt * 3 * t.D * 2);
-    upd(Tt * static_cast<size_t>(c.t_mlp) * cs);
+    size_t tb = Tt * 3 * t.D * 2;
+    if (Tt * static_cast<size_t>(c.t_mlp) * cs > tb) tb = Tt * static_cast<size_t>(c.t_mlp) * cs;
+    void* q = nullptr;
+    if ((rc = m->pool.alloc(&q, Tt * t.D * sizeof(float)))) return rc; m->wt.x = static_cast<float*>(q);
+    if ((rc = m->pool.alloc(&m->wt.h, Tt * t.D * cs))) return rc;
+    if ((rc = m->pool.alloc(&m->wt.big, tb))) return rc;
+    if ((rc = m->pool.alloc(&m->wt.pooled, Bm * t.D * cs))) return rc;
+    if ((rc = m->pool.alloc(&q, Bm * sizeof(int)))) return rc; m->wt.idx = static_cast<int*>(q);
   }
   const size_t E = dual ? t.D : vision_out_dim(m);
   void* p = nullptr;
@@ -799,6 +826,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
     const size_t gb = static_cast<size_t>(m->graph_max_batch) < Bm ? m->graph_max_batch : Bm;
     if ((rc = m->pool.alloc(&p, gb * gw * sizeof(float)))) return rc;
     m->graph_out = static_cast<float*>(p);
+    if (dual) { if ((rc = m->pool.alloc(&p, gb * gw * sizeof(float)))) return rc; m->graph_out_t = static_cast<float*>(p); }
   }
 
   // ---- GEMM plans (TMA descriptors bound to the fixed workspace / weight buffers) ----
@@ -814,7 +842,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
     e.rows_in = v.n; e.rows_out = v.S; e.row_off = v.pooling == JIMM_POOL_CLS ? 1 : 0; e.mode = 0;
     JIMM_TRY(gemm_plan_init(&v.p_patch, m->cdt, ws.big, PPC, v.patch.w, PPC, static_cast<int>(Bm) * v.n, D, PPC, e));
   }
-  JIMM_TRY(plan_encoder(m, &v.enc, static_cast<int>(Tv)));
+  JIMM_TRY(plan_encoder(m, &v.enc, static_cast<int>(Tv), EncBufs{ws.x, ws.h, ws.big}));
   if (v.head.N > 0)
     JIMM_TRY(gemm_plan_init(&v.p_head, m->cdt, ws.pooled, D, v.head.w, D, static_cast<int>(Bm), v.head.N, D,
                             epi_plain(v.head, ACT_NONE, ws.out_dev, DT_F32, v.head.N, 0)));
@@ -830,8 +858,8 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
     JIMM_TRY(gemm_plan_init(&v.p_map_fc2, m->cdt, ws.mid2, 4 * D, v.map_fc2.w, 4 * D, static_cast<int>(Bm), D, 4 * D, e));
   }
   if (dual) {
-    JIMM_TRY(plan_encoder(m, &t.enc, static_cast<int>(Bm) * t.T));
-    JIMM_TRY(gemm_plan_init(&t.p_head, m->cdt, ws.pooled, t.D, t.head.w, t.D, static_cast<int>(Bm), t.D, t.D,
+    JIMM_TRY(plan_encoder(m, &t.enc, static_cast<int>(Bm) * t.T, EncBufs{m->wt.x, m->wt.h, m->wt.big}));
+    JIMM_TRY(gemm_plan_init(&t.p_head, m->cdt, m->wt.pooled, t.D, t.head.w, t.D, static_cast<int>(Bm), t.D, t.D,
                             epi_plain(t.head, ACT_NONE, ws.out_dev, DT_F32, t.D, 0)));
   }
   JIMM_CUDA_CHECK(cudaDeviceSynchronize());
@@ -847,6 +875,7 @@ int jimm_model_destroy(jimm_model_t* m) {
   comm_destroy(&m->comm);
   graphs_release(m);
   if (m->capture_stream) cudaStreamDestroy(m->capture_stream);
+  if (m->text_stream) { cudaStreamDestroy(m->text_stream); cudaEventDestroy(m->ev_fork); cudaEventDestroy(m->ev_join); }
   for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
   if (m->copy_stream) {
     cudaStreamDestroy(m->copy_stream);
@@ -922,12 +951,50 @@ int jimm_contrastive_logits(jimm_model_t* m, const float* img_e, int Bi, const f
   return logits_run(m->ws.nrm_i, m->ws.nrm_t, m->logit_scale, m->logit_bias, logits, Bi, Bt, E, Bt, s);
 }
 
+// Fork the text tower onto the model's side stream (ordered after everything already enqueued on `s`), returning the stream it runs
+// on; join_text() makes `s` wait for it.  Profiling (per-GEMM events) and JIMM_DUAL_STREAMS=0 keep the towers on one stream.
+static int fork_text(jimm_model* m, cudaStream_t s, cudaStream_t* ts) {
+  *ts = s;
+  if (!m->dual_streams || m->prof_on) return 0;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return 0; }
+  if (!m->text_stream) {
+    JIMM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->text_stream, cudaStreamNonBlocking));
+    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+    JIMM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+  }
+  JIMM_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+  JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->text_stream, m->ev_fork, 0));
+  *ts = m->text_stream;
+  return 0;
+}
+static int join_text(jimm_model* m, cudaStream_t s, cudaStream_t ts) {
+  if (ts == s) return 0;
+  JIMM_CUDA_CHECK(cudaEventRecord(m->ev_join, ts));
+  JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0));
+  return 0;
+}
+
+// encode_image + encode_text of one call, the two towers running concurrently (device inputs); img_e fp32 [Bi,E], txt_e fp32 [Bt,E].
+int jimm_dual_encode(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* img_e, float* txt_e,
+                     void* stream) {
+  JIMM_TRY(check_ready(m, Bi));
+  if (!m->txt.present) { set_last_error("model has no text tower"); return JIMM_EINVAL; }
+  if (in_dtype < JIMM_F32 || in_dtype > JIMM_BF16) { set_last_error("bad image dtype %d", in_dtype); return JIMM_EINVAL; }
+  if (T <= 0 || T > m->txt.T) { set_last_error("sequence length %d outside (0, context_length=%d]", T, m->txt.T); return JIMM_EINVAL; }
+  JIMM_TRY(set_device(m));
+  cudaStream_t s = static_cast<cudaStream_t>(stream), ts = s;
+  JIMM_TRY(fork_text(m, s, &ts));
+  JIMM_TRY(text_chunks(m, ids, Bt, T, txt_e, ts));
+  JIMM_TRY(vision_chunks(m, img, in_dtype, Bi, img_e, s));
+  return join_text(m, s, ts);
+}
+
 int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* logits,
                       void* stream) {
   JIMM_TRY(check_ready(m, Bi));
   if (Bi > m->max_batch || Bt > m->max_batch) { set_last_error("dual_forward: batch (%d,%d) exceeds max_batch %d", Bi, Bt, m->max_batch); return JIMM_EINVAL; }
-  JIMM_TRY(jimm_encode_image(m, img, in_dtype, Bi, m->ws.emb_i, stream));
-  JIMM_TRY(jimm_encode_text(m, ids, Bt, T, m->ws.emb_t, stream));
+  JIMM_TRY(jimm_dual_encode(m, img, in_dtype, Bi, ids, Bt, T, m->ws.emb_i, m->ws.emb_t, stream));
   return jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, logits, stream);
 }
 
@@ -1100,7 +1167,9 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
   m->host_chain = false;
   JIMM_CUDA_CHECK(cudaEventRecord(m->ev_start, s));
   JIMM_CUDA_CHECK(cudaStreamWaitEvent(m->copy_stream, m->ev_start, 0));
-  JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids_host, static_cast<size_t>(Bt) * T * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  cudaStream_t ts = s;
+  JIMM_TRY(fork_text(m, s, &ts));  // ids copy + text tower on the side stream, concurrently with the image copy and the vision tower
+  JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.in_ids, ids_host, static_cast<size_t>(Bt) * T * sizeof(int32_t), cudaMemcpyHostToDevice, ts));
   int sizes[jimm_model::kHostSlices] = {Bi, 0, 0, 0};
   if (getenv("JIMM_HOST_SLICES")) host_slices(m, Bi, sizes);
   int off = 0;
@@ -1113,7 +1182,7 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
     JIMM_CUDA_CHECK(cudaEventRecord(m->ev_copied[slot], m->copy_stream));
     off += n;
   }
-  JIMM_TRY(exec_text(m, m->ws.in_ids, Bt, T, m->ws.emb_t, s));
+  JIMM_TRY(exec_text(m, m->ws.in_ids, Bt, T, m->ws.emb_t, ts));
   off = 0;
   for (int slot = 0; slot < jimm_model::kHostSlices; ++slot) {
     const int n = sizes[slot];
@@ -1123,6 +1192,7 @@ int jimm_dual_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, 
     JIMM_TRY(exec_vision(m, src, in_dtype, n, m->ws.emb_i + static_cast<size_t>(off) * E, s));
     off += n;
   }
+  JIMM_TRY(join_text(m, s, ts));
   JIMM_TRY(jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, m->ws.out_dev, stream));
   JIMM_CUDA_CHECK(cudaMemcpyAsync(logits_host, m->ws.out_dev, static_cast<size_t>(Bi) * Bt * sizeof(float), cudaMemcpyDeviceToHost, s));
   return 0;

@@ -103,11 +103,13 @@ class DualTower(_NativeOwner, nn.Module):
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     x_d = x.to(n.device, non_blocking=True)
-            te = n.text(ids_d)
-            if not x.is_cuda:
+            if x.is_cuda:
+                ie, te = n.dual_encode(x_d, ids_d)  # both towers concurrently (text forked onto the library's side stream)
+            else:
+                te = n.text(ids_d)
                 cur.wait_stream(side)
                 x_d.record_stream(cur)
-            ie = n.vision(x_d, encode=True)
+                ie = n.vision(x_d, encode=True)
             out = self._distributed_logits(n, ie, te, B)
             if not host_in:
                 return out
