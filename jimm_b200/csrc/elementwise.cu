@@ -159,12 +159,56 @@ static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P,
   return 0;
 }
 
-int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rows_per_sample) {
-  if ((P * C) % 4 != 0 || (W * C) % 4 != 0) {
-    set_last_error("patchify: patch_size*channels (%d) and width*channels (%d) must be multiples of 4", P * C, W * C);
-    return -1;
+// Generic form (any patch size / channel count, zero-padded K): one thread per OUTPUT element (b, patch, k), k in [0, ldk); columns
+// k >= P*P*C are written as zeros so that the row stride ldk can be rounded up to the 16 bytes TMA needs (patch 14 x 3 channels = 588
+// elements -> 592: every ViT-L/14 / H/14 CLIP and patch14 SigLIP checkpoint the reference loads).
+template <typename InT, typename OutT>
+__global__ void __launch_bounds__(256)
+patchify_generic_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int H, int W, int C, int P, int gh, int gw, int rps, int ldk,
+                        size_t total) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = static_cast<int>(i % ldk);
+  const size_t r = i / ldk;
+  const int n = gh * gw;
+  const int b = static_cast<int>(r / n), pt = static_cast<int>(r - static_cast<size_t>(b) * n);
+  const int gy = pt / gw, gx = pt - gy * gw;
+  float v = 0.f;
+  const int PC = P * C;
+  if (k < P * PC) {
+    const int ky = k / PC, kc = k - ky * PC;  // (kh, kw, c) order == the HWIO kernel reshape
+    v = to_float(img[(static_cast<size_t>(b) * H + gy * P + ky) * W * C + static_cast<size_t>(gx) * PC + kc]);
   }
+  out[(static_cast<size_t>(b) * rps + pt) * ldk + k] = from_float<OutT>(v);
+}
+
+template <typename InT>
+static int patchify_generic_dispatch(const void* img, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rps, int ldk) {
+  const int gh = H / P, gw = W / P;
+  if (rps <= 0) rps = gh * gw;
+  const size_t total = static_cast<size_t>(B) * gh * gw * ldk;
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  const InT* in = static_cast<const InT*>(img);
+  if (out_type == DT_F32) patchify_generic_kernel<InT, float><<<grid, 256, 0, stream>>>(in, static_cast<float*>(out), H, W, C, P, gh, gw, rps, ldk, total);
+  else if (out_type == DT_TF32) patchify_generic_kernel<InT, tf32_t><<<grid, 256, 0, stream>>>(in, static_cast<tf32_t*>(out), H, W, C, P, gh, gw, rps, ldk, total);
+  else if (out_type == DT_F16) patchify_generic_kernel<InT, __half><<<grid, 256, 0, stream>>>(in, static_cast<__half*>(out), H, W, C, P, gh, gw, rps, ldk, total);
+  else patchify_generic_kernel<InT, __nv_bfloat16><<<grid, 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), H, W, C, P, gh, gw, rps, ldk, total);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
+// ldk: row stride of `out` in elements (0 = P*P*C).  The vectorised kernel needs P*C and W*C to be multiples of 4 and an unpadded row.
+int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rows_per_sample,
+                 int ldk) {
   if (B <= 0) return 0;
+  const int PPC = P * P * C;
+  if (ldk <= 0) ldk = PPC;
+  if (ldk < PPC) { set_last_error("patchify: row stride %d < patch_size^2*channels %d", ldk, PPC); return -1; }
+  if ((P * C) % 4 != 0 || (W * C) % 4 != 0 || ldk != PPC) {
+    if (in_type == DT_F32) return patchify_generic_dispatch<float>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample, ldk);
+    if (in_type == DT_F16) return patchify_generic_dispatch<__half>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample, ldk);
+    return patchify_generic_dispatch<__nv_bfloat16>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample, ldk);
+  }
   if (in_type == DT_F32) return patchify_dispatch<float>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);
   if (in_type == DT_F16) return patchify_dispatch<__half>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);
   return patchify_dispatch<__nv_bfloat16>(img, B, H, W, C, P, out, out_type, stream, rows_per_sample);

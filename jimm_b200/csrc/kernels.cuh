@@ -19,7 +19,8 @@ int layernorm_run(const float* x, int ldx, int group, int row_off, const int* ro
 // Patchify: NHWC image (in_type fp32/fp16/bf16) -> A matrix [B*gh*gw, P*P*C] of out_type, row order (b,gy,gx), column
 // order (ky,kx,c) == the HWIO kernel reshape (common/vit.py:153-165,228-230).  128-bit loads.
 int patchify_run(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream,
-                 int rows_per_sample = 0 /* 0 = gh*gw; larger = padded row count per sample (pad rows untouched) */);
+                 int rows_per_sample = 0 /* 0 = gh*gw; larger = padded row count per sample (pad rows untouched) */,
+                 int ldk = 0 /* row stride in elements; 0 = P*P*C; larger = zero-padded K (any P / C through the generic kernel) */);
 
 // x[b, s, :] = pos[s, :] (+ cls for s == 0)   -- initial value of the residual stream; the patch GEMM then reduce-adds the
 // patch embeddings into rows tok_off.. (common/vit.py:231-236)

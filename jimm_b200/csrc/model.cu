@@ -113,6 +113,7 @@ struct Encoder {
 struct VisionTower {
   bool present = false;
   int img = 0, P = 0, C = 0, D = 0, n = 0, n_pad = 0, S = 0, pooling = 0, pre_norm = 0, patch_bias = 0;
+  int Kp = 0;  // patch GEMM K = P*P*C rounded up to a multiple of 8 (16-byte rows for TMA; the pad columns are zeros on both operands)
   bool patch_scatter = false;  // patch GEMM reduce-adds into the pos-initialised residual stream through a 3-D TMA map
   float eps_outer = 1e-5f;
   Encoder enc;
@@ -293,14 +294,15 @@ struct Packer {
     return 0;
   }
   // flax kernel viewed as (K, N) row-major  ->  rows [n0, n0+N) of a packed [Ntot, K] K-major operand
-  int pack_kernel(const std::string& name, std::initializer_list<int64_t> shape, int K, int N, void* dst_base, int n0) {
+  int pack_kernel(const std::string& name, std::initializer_list<int64_t> shape, int K, int N, void* dst_base, int n0, int ldd = 0) {
+    if (ldd <= 0) ldd = K;
     HostParam* hp = find(name, shape);
     if (!hp) return JIMM_ESTATE;
     if (hp->numel() != static_cast<size_t>(K) * N) { set_last_error("finalize: '%s' numel mismatch", name.c_str()); return JIMM_ESTATE; }
     JIMM_TRY(ensure_stage(hp->numel()));
     JIMM_CUDA_CHECK(cudaMemcpyAsync(stage, hp->data.data(), hp->numel() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    uint8_t* dst = static_cast<uint8_t*>(dst_base) + static_cast<size_t>(n0) * K * cdt_size(m);
-    JIMM_TRY(transpose_cast_run(stage, K, N, dst, m->cdt, K, stream));
+    uint8_t* dst = static_cast<uint8_t*>(dst_base) + static_cast<size_t>(n0) * ldd * cdt_size(m);
+    JIMM_TRY(transpose_cast_run(stage, K, N, dst, m->cdt, ldd, stream));
     JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
     return 0;
   }
@@ -450,10 +452,10 @@ static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float
   // patch embed + pos (+cls)
   if (v.patch_scatter) {
     JIMM_TRY(tokens_init_run(ws.x, v.pooling == JIMM_POOL_CLS ? v.cls : nullptr, v.pos, B, S, D, s));
-    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s, v.n_pad));
+    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s, v.n_pad, v.Kp));
     JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * v.n_pad, s));
   } else {
-    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s));
+    JIMM_TRY(patchify_run(img, in_dtype, B, v.img, v.img, v.C, v.P, ws.big, m->cdt, s, 0, v.Kp));
     JIMM_TRY(run_gemm(m, v.p_patch, ws.big, v.patch.K, v.patch, B * n, s));
     if (v.pooling == JIMM_POOL_CLS) JIMM_TRY(cls_row_run(ws.x, v.cls, v.pos, B, S, D, s));
   }
@@ -631,8 +633,18 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
     return JIMM_EINVAL;
   }
   if (cfg->compute_dtype < JIMM_F32 || cfg->compute_dtype > JIMM_BF16) { set_last_error("bad compute_dtype"); return JIMM_EINVAL; }
-  if (cfg->patch <= 0 || cfg->img_size < cfg->patch || (cfg->patch * cfg->in_ch) % 4 != 0) {
-    set_last_error("unsupported patch/img/channels (%d/%d/%d): patch*channels must be a multiple of 4", cfg->patch, cfg->img_size, cfg->in_ch);
+  if (cfg->patch <= 0 || cfg->img_size < cfg->patch || cfg->in_ch <= 0) {
+    set_last_error("unsupported patch/img/channels (%d/%d/%d)", cfg->patch, cfg->img_size, cfg->in_ch);
+    return JIMM_EINVAL;
+  }
+  // limits of the kernels, reported at construction (not on the first forward): widths are TMA rows (16-byte multiples), LayerNorm keeps
+  // a row in registers
+  if (cfg->v_width % 8 != 0 || cfg->v_mlp % 8 != 0 || cfg->v_width > 2048) {
+    set_last_error("vision width %d / mlp %d: must be multiples of 8 and width <= 2048", cfg->v_width, cfg->v_mlp);
+    return JIMM_EINVAL;
+  }
+  if (dual && (cfg->t_width % 8 != 0 || cfg->t_mlp % 8 != 0 || cfg->t_width > 2048)) {
+    set_last_error("text width %d / mlp %d: must be multiples of 8 and width <= 2048", cfg->t_width, cfg->t_mlp);
     return JIMM_EINVAL;
   }
   int ndev = 0;
@@ -717,10 +729,12 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   v.patch_scatter = !m->simt && m->epi_mode_res == 2;
   v.enc.c.D = c.v_width; v.enc.c.H = c.v_heads; v.enc.c.M = c.v_mlp; v.enc.c.L = c.v_layers;
   v.enc.c.act = c.v_act; v.enc.c.causal = 0; v.enc.c.eps = c.v_eps_block;
-  const int D = v.D, PPC = c.patch * c.patch * c.in_ch;
-  if (PPC % 8 != 0 || D % 8 != 0 || c.v_mlp % 8 != 0) { set_last_error("dims must be multiples of 8"); return JIMM_EINVAL; }
+  const int D = v.D, PPC0 = c.patch * c.patch * c.in_ch;
+  const int PPC = (PPC0 + 7) / 8 * 8;  // K of the patch GEMM, zero-padded (patch 14: 588 -> 592)
+  v.Kp = PPC;
   if ((rc = pk.alloc_linear(&v.patch, D, PPC, c.patch_bias != 0))) return fail(rc);
-  if ((rc = pk.pack_kernel(vp + "patch_embeddings.kernel", {c.patch, c.patch, c.in_ch, D}, PPC, D, v.patch.w, 0))) return fail(rc);
+  if (PPC != PPC0) JIMM_CUDA_CHECK(cudaMemsetAsync(v.patch.w, 0, static_cast<size_t>(D) * PPC * cdt_size(m), pk.stream));
+  if ((rc = pk.pack_kernel(vp + "patch_embeddings.kernel", {c.patch, c.patch, c.in_ch, D}, PPC0, D, v.patch.w, 0, PPC))) return fail(rc);
   if (c.patch_bias && (rc = pk.upload_bias_at(vp + "patch_embeddings.bias", {D}, v.patch.b, D))) return fail(rc);
   if (v.pooling == JIMM_POOL_CLS && (rc = pk.upload_f32(vp + "cls_token", {1, 1, D}, &v.cls))) return fail(rc);
   if ((rc = pk.upload_f32(vp + "position_embeddings", {1, v.S, D}, &v.pos))) return fail(rc);
@@ -1014,7 +1028,7 @@ static int ensure_copy_stream(jimm_model* m) {
 // one, chosen between nb/head_div and nb/3 so that BOTH slices quantise well into waves of 256-row pair tiles (a badly chosen
 // split costs an extra wave in every GEMM: 64 images take 3.3 ms on ViT-B/16 where 62 take 2.8 ms).  JIMM_HOST_SLICES (comma
 // separated sizes) overrides it for experiments.
-static void host_slices(const jimm_model* m, int nb, int* sizes) {
+static void host_slices(const jimm_model* m, int nb, int* sizes, size_t bytes_per_image = 0) {
   for (int i = 0; i < jimm_model::kHostSlices; ++i) sizes[i] = 0;
   sizes[0] = nb;
   if (const char* env = getenv("JIMM_HOST_SLICES")) {
@@ -1031,6 +1045,10 @@ static void host_slices(const jimm_model* m, int nb, int* sizes) {
     return;
   }
   if (nb < 128) return;
+  // Slicing hides all but the first slice's copy but costs GEMM waves and launches (~0.45 ms on ViT-B/16 at 256 images): only worth it
+  // when the whole copy is long.  Raw uint8 frames (38 MB for 256 x 224 x 224 x 3, 0.7 ms over PCIe) go in one piece: measured 10.82 ms
+  // unsliced against 11.28 ms sliced, device-resident 10.35 ms (scripts/gpu_e2e_probe.py).
+  if (bytes_per_image && static_cast<size_t>(nb) * bytes_per_image < (static_cast<size_t>(64) << 20)) return;
   static int head_div = -1;
   if (head_div < 0) { const char* env = getenv("JIMM_HOST_HEAD_DIV"); head_div = (env && atoi(env) > 0) ? atoi(env) : 4; }
   const int S = m->vis.S, D = m->vis.D, Mm = m->vis.enc.c.M;
@@ -1079,7 +1097,7 @@ static int vit_forward_host_impl(jimm_model_t* m, const void* img_host, int in_d
   for (int b0 = 0; b0 < B; b0 += m->max_batch) {
     const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
     int sizes[jimm_model::kHostSlices];
-    host_slices(m, nb, sizes);
+    host_slices(m, nb, sizes, src_bytes);
     bool same_layout = m->host_chain && m->host_chain_stream == s && m->host_chain_kind == kind;
     for (int i = 0; i < jimm_model::kHostSlices; ++i) same_layout = same_layout && sizes[i] == m->host_chain_sizes[i];
     if (!same_layout) {

@@ -214,6 +214,28 @@ def test_tower_map_pooling_other_dtypes(dtype):
         check_parity("MAP tower 2x256 @64", "pooled", dtype, "fp32", out, ref, BF16_VS_FP32)
 
 
+@pytest.mark.parametrize("patch,chans,pooling", [(14, 3, "CLS"), (14, 3, "MAP"), (7, 1, "CLS")])
+def test_tower_patch14_and_odd_channels(patch, chans, pooling):
+    """Patch sizes / channel counts whose patch row (P*P*C elements) is not a multiple of 8 -- every ViT-L/14, ViT-H/14 CLIP and patch14
+    SigLIP checkpoint (14*14*3 = 588): K of the patch GEMM is zero-padded to a 16-byte row on both operands."""
+    from jimm_b200.common.vit import VisionTransformerBase
+
+    img = patch * 4
+    t = O.TowerCfg(img_size=img, patch_size=patch, in_channels=chans, hidden_size=128, num_layers=2, num_heads=2, mlp_dim=512,
+                   pooling_type=pooling, use_quick_gelu=pooling == "CLS", use_pre_norm=pooling == "CLS", use_patch_bias=pooling == "MAP",
+                   layernorm_epsilon=1e-5)
+    p = O.random_tower_params(t, seed=31)
+    x = O.synthetic_images(5, img, C=chans)
+    with torch.no_grad():
+        ref = O.vision_tower(p, "", x, t)
+    for dtype in (torch.float16, torch.float32):
+        m = _set(VisionTransformerBase(img_size=img, patch_size=patch, in_channels=chans, hidden_size=128, num_layers=2, num_heads=2, mlp_dim=512,
+                                       pooling_type=pooling, use_quick_gelu=pooling == "CLS", use_pre_norm=pooling == "CLS",
+                                       use_patch_bias=pooling == "MAP", layernorm_epsilon=1e-5, dtype=dtype), p)
+        check_parity(f"tower patch {patch} x {chans} ch, {pooling}", "pooled", dtype, "fp32", m(x.cuda()), ref, TOL)
+        assert torch.equal(m(x), m(x.cuda()).cpu())  # host path
+
+
 def test_config3_shape_vit_l16_384_map_bf16_reduced_depth():
     """BASELINE config 3 shapes (ViT-L/16 @384, MAP head, bf16; S = 576 -> two-pass tcgen05 attention) with 2 of the 24 layers."""
     from jimm_b200.common.vit import VisionTransformerBase
