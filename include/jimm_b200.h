@@ -35,7 +35,11 @@ typedef struct jimm_model jimm_model_t;
 
 enum jimm_status { JIMM_OK = 0, JIMM_EINVAL = -1, JIMM_ECUDA = -2, JIMM_EDRIVER = -3, JIMM_ESTATE = -4, JIMM_ENOMEM = -5 };
 enum jimm_dtype { JIMM_F32 = 0, JIMM_F16 = 1, JIMM_BF16 = 2, JIMM_I32 = 3 };
-enum jimm_kind { JIMM_VIT = 0, JIMM_CLIP = 1, JIMM_SIGLIP = 2, JIMM_TOWER = 3 /* bare VisionTransformerBase */ };
+enum jimm_kind {
+  JIMM_VIT = 0, JIMM_CLIP = 1, JIMM_SIGLIP = 2, JIMM_TOWER = 3 /* bare VisionTransformerBase */,
+  JIMM_ENCODER = 4 /* bare Transformer / TransformerEncoder stack (common/transformer.py:22-196) */,
+  JIMM_MAPHEAD = 5 /* bare MultiHeadAttentionPoolingHead (common/vit.py:12-101) */
+};
 enum jimm_pool { JIMM_POOL_CLS = 0, JIMM_POOL_MAP = 1 };
 enum jimm_act { JIMM_GELU_TANH = 0, JIMM_QUICK_GELU = 1 };
 enum jimm_text_pool { JIMM_TPOOL_EOT_ARGMAX = 0, JIMM_TPOOL_LAST = 1 };
@@ -99,6 +103,14 @@ JIMM_API int jimm_dual_encode(jimm_model_t* m, const void* img, int in_dtype, in
 JIMM_API int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, const int32_t* ids, int Bt, int T, float* logits,
                       void* stream);
 
+/* -- forward of a bare sub-module (kinds JIMM_ENCODER / JIMM_MAPHEAD; config fields used: v_width, v_heads, v_mlp, v_layers, v_act,
+ *    v_eps_block, v_eps_outer, t_causal (attn_mask = tril), ctx_len = max tokens per sample, compute_dtype; parameters keyed
+ *    "blocks.layers.{i}.<...>" resp. "probe", "attn.<...>", "layernorm.<...>", "mlp.layers.{0,2}.<...>") ---------------------------- */
+/* Transformer.__call__ / TransformerEncoder.__call__ (common/transformer.py:116-132,190-196): x, out device fp32 [B,S,D]. */
+JIMM_API int jimm_encoder_forward(jimm_model_t* m, const float* x, int B, int S, float* out, void* stream);
+/* MultiHeadAttentionPoolingHead.__call__ (common/vit.py:87-101): x device fp32 [B,S,D] -> out device fp32 [B,D]. */
+JIMM_API int jimm_map_head_forward(jimm_model_t* m, const float* x, int B, int S, float* out, void* stream);
+
 /* -- forward: HOST buffers (the reference-facing call: host->device copy, forward, device->host copy, all enqueued on
  *    `stream`; the caller synchronises the stream before reading `out`).  examples/vit_inference.py:52-58. ----------- */
 JIMM_API int jimm_vit_forward_host(jimm_model_t* m, const void* img_host, int in_dtype, int B, float* out_host, void* stream);
@@ -140,6 +152,8 @@ JIMM_API int jimm_k_layernorm(const float* x, int ldx, int group, int row_off, c
 JIMM_API int jimm_k_attention(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, void* stream);
 JIMM_API int jimm_k_map_attention(const float* q, const void* kv, int io_type, void* out, int out_type, int B, int S, int H, void* stream);
 JIMM_API int jimm_k_patchify(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, void* stream);
+/* y = act(x) elementwise on device fp32 (act: 1 tanh-GELU == nnx.gelu, 2 QuickGELU == common/transformer.py:12-19). */
+JIMM_API int jimm_k_activation(const float* x, float* y, long long n, int act, void* stream);
 JIMM_API int jimm_k_embed(const int32_t* ids, const float* table, const float* pos, float* x, int B, int T, int D, int vocab, void* stream);
 JIMM_API int jimm_k_l2_normalize(const float* x, float* out, int ldo, int B, int E, void* stream);
 JIMM_API int jimm_k_logits(const float* img, const float* txt, const float* logit_scale, const float* logit_bias, float* logits, int Bi, int Bt,

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjimm_b200.so")
 
 F32, F16, BF16, I32 = 0, 1, 2, 3
-KIND_VIT, KIND_CLIP, KIND_SIGLIP, KIND_TOWER = 0, 1, 2, 3
+KIND_VIT, KIND_CLIP, KIND_SIGLIP, KIND_TOWER, KIND_ENCODER, KIND_MAPHEAD = 0, 1, 2, 3, 4, 5
 POOL_CLS, POOL_MAP = 0, 1
 ACT_GELU_TANH, ACT_QUICK_GELU = 0, 1
 TPOOL_EOT_ARGMAX, TPOOL_LAST = 0, 1
@@ -64,6 +64,8 @@ SIGNATURES = {
     "jimm_contrastive_logits": (_i, [_vp, _fp, _i, _fp, _i, _fp, _vp]),
     "jimm_dual_encode": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _fp, _vp]),
     "jimm_dual_forward": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),
+    "jimm_encoder_forward": (_i, [_vp, _fp, _i, _i, _fp, _vp]),
+    "jimm_map_head_forward": (_i, [_vp, _fp, _i, _i, _fp, _vp]),
     "jimm_vit_forward_host": (_i, [_vp, _vp, _i, _i, _fp, _vp]),
     "jimm_dual_forward_host": (_i, [_vp, _vp, _i, _i, _ip, _i, _i, _fp, _vp]),
     "jimm_vit_forward_host_u8": (_i, [_vp, _vp, _vp, _i, _i, _i, _fp, _vp]),
@@ -79,6 +81,7 @@ SIGNATURES = {
     "jimm_k_attention": (_i, [_vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "jimm_k_map_attention": (_i, [_fp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "jimm_k_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "jimm_k_activation": (_i, [_fp, _fp, C.c_longlong, _i, _vp]),
     "jimm_k_embed": (_i, [_ip, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),
     "jimm_k_l2_normalize": (_i, [_fp, _fp, _i, _i, _i, _vp]),
     "jimm_k_logits": (_i, [_fp, _fp, _fp, _fp, _fp, _i, _i, _i, _i, _vp]),

@@ -263,5 +263,49 @@ class NativeModel:
         return out
 
 
+class NativeSubModule:
+    """Native handle of a bare Transformer / TransformerEncoder (kind ENCODER) or MultiHeadAttentionPoolingHead (kind MAPHEAD): the
+    same kernels and block orchestration as inside a tower, on [batch, seq, hidden] activations."""
+
+    def __init__(self, cfg: _lib.Config, params: Dict[str, torch.Tensor], max_batch: int):
+        self.native = NativeModel(cfg, params, max_batch)
+        self.kind, self.max_seq, self.max_batch, self.D = cfg.kind, cfg.ctx_len, int(max_batch), cfg.v_width
+
+    def close(self):
+        self.native.close()
+
+    def __call__(self, x) -> torch.Tensor:
+        n = self.native
+        x = _as_tensor(x, "activations")
+        if x.ndim != 3 or x.shape[2] != self.D:
+            raise ValueError(f"expected activations of shape [batch, seq, {self.D}], got {tuple(x.shape)}")
+        host = not x.is_cuda
+        B, S, D = x.shape
+        with torch.cuda.device(n.device):
+            xd = x.to(n.device, torch.float32, non_blocking=True).contiguous()
+            st = C.c_void_p(_stream_ptr(n.device))
+            if self.kind == _lib.KIND_ENCODER:
+                out = torch.empty((B, S, D), dtype=torch.float32, device=n.device)
+                _lib.check(n.lib.jimm_encoder_forward(n.handle, C.c_void_p(xd.data_ptr()), B, S, C.c_void_p(out.data_ptr()), st))
+            else:
+                out = torch.empty((B, D), dtype=torch.float32, device=n.device)
+                _lib.check(n.lib.jimm_map_head_forward(n.handle, C.c_void_p(xd.data_ptr()), B, S, C.c_void_p(out.data_ptr()), st))
+            xd.record_stream(torch.cuda.current_stream(n.device))
+        return out.cpu() if host else out
+
+
+def activation(x, act: int) -> torch.Tensor:
+    """Elementwise activation kernel (1 tanh-GELU, 2 QuickGELU) on a CUDA tensor; fp32 result."""
+    x = _as_tensor(x, "x")
+    if not x.is_cuda:
+        raise _lib.JimmError("jimm_b200 runs on CUDA tensors only (there is no CPU fallback)")
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        xd = x.to(torch.float32).contiguous()
+        y = torch.empty_like(xd)
+        _lib.check(lib.jimm_k_activation(C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), xd.numel(), int(act), C.c_void_p(_stream_ptr(x.device))))
+    return y
+
+
 def default_max_batch() -> int:
     return int(os.environ.get("JIMM_MAX_BATCH", "256"))

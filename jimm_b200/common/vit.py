@@ -10,18 +10,23 @@ import torch
 
 from .. import _lib, nn
 from .._runtime import NativeModel, default_max_batch
-from .transformer import Transformer, g_wrap
+from .transformer import Transformer, _SubModuleRunner, g_wrap
 
 
-class MultiHeadAttentionPoolingHead(nn.Module):
-    """common/vit.py:12-101.  Parameter holder; evaluated inside the tower forward (probe query precomputed at
-    finalize, k/v projection GEMM over all tokens, single-query attention, LN + MLP(4x) + residual)."""
+class MultiHeadAttentionPoolingHead(_SubModuleRunner, nn.Module):
+    """common/vit.py:12-101.  Inside a tower it is evaluated as part of the tower forward (probe query precomputed at finalize, k/v
+    projection GEMM over all tokens, single-query attention, LN + MLP + residual); called on its own it runs the same kernels through
+    jimm_map_head_forward."""
 
     def __init__(self, hidden_size: int, intermediate_size: int, num_heads: int, layernorm_epsilon: float = 1e-6, rngs=None,
                  dtype=None, param_dtype=None, mesh=None):
-        super().__init__()
+        nn.Module.__init__(self)
+        self._sub_init(dtype)
+        if intermediate_size != 4 * hidden_size:
+            raise ValueError("the MAP head kernels take intermediate_size == 4 * hidden_size (the only value the reference uses, common/vit.py:175)")
         g = nn._gen(rngs)
         object.__setattr__(self, "layernorm_epsilon", layernorm_epsilon)
+        object.__setattr__(self, "_dims", (hidden_size, num_heads))
         self.add_param("probe", nn.zeros((1, 1, hidden_size)))
         self.add_child("attn", nn.MultiHeadAttention(num_heads, hidden_size, rngs=g_wrap(g)))
         self.add_child("layernorm", nn.LayerNorm(hidden_size, layernorm_epsilon))
@@ -29,8 +34,19 @@ class MultiHeadAttentionPoolingHead(nn.Module):
         self.add_child("mlp", nn.Sequential(nn.Linear(hidden_size, intermediate_size, rngs=g_wrap(g)), None,
                                             nn.Linear(intermediate_size, hidden_size, rngs=g_wrap(g))))
 
+    def _sub_config(self, max_seq):
+        D, H = self._dims
+        cfg = _lib.Config()
+        cfg.kind = _lib.KIND_MAPHEAD
+        cfg.v_width, cfg.v_heads, cfg.v_mlp, cfg.v_layers = D, H, 4 * D, 0
+        cfg.v_eps_outer = cfg.v_eps_block = float(self.layernorm_epsilon)
+        cfg.ctx_len = int(max_seq)
+        cfg.compute_dtype = self._sub_dtype
+        return cfg
+
     def __call__(self, hidden_state):
-        raise NotImplementedError("MultiHeadAttentionPoolingHead runs inside the CUDA library as part of VisionTransformerBase")
+        """[batch, seq, hidden] -> [batch, hidden] (common/vit.py:87-101)."""
+        return self._run(hidden_state)
 
 
 class _NativeOwner:

@@ -366,6 +366,18 @@ int transpose_cast_run(const float* src, int K, int N, void* dst, int out_type, 
   return 0;
 }
 
+// standalone activation (API parity for jimm.common.transformer.quickgelu; inside the towers the activation is the FC1 epilogue)
+__global__ void activation_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n, int act) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = act == 2 ? quick_gelu(x[i]) : (act == 1 ? gelu_tanh(x[i]) : x[i]);
+}
+int activation_run(const float* x, float* y, size_t n, int act, cudaStream_t stream) {
+  if (n == 0) return 0;
+  activation_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(x, y, n, act);
+  JIMM_LAUNCH_CHECK();
+  return 0;
+}
+
 template <typename OutT>
 __global__ void cast_kernel(const float* __restrict__ src, OutT* __restrict__ dst, size_t n) {
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;

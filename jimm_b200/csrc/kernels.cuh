@@ -45,6 +45,7 @@ int logits_run(const float* img, const float* txt, const float* logit_scale, con
 // dst[n*K + k] = cast(src[k*N + n])   (flax (in,out) kernel -> K-major [N,K] operand)
 int transpose_cast_run(const float* src, int K, int N, void* dst, int out_type, int ldd, cudaStream_t stream);
 int cast_run(const float* src, void* dst, int out_type, size_t n, cudaStream_t stream);
+int activation_run(const float* x, float* y, size_t n, int act /* 0 none, 1 gelu_tanh, 2 quick_gelu */, cudaStream_t stream);
 
 // Multi-head softmax attention over the fused qkv buffer [B*S, 3D] (q | k | v, heads of 64).  SURVEY 8a row a5.
 //   o[b*S+s, h*64+d] = softmax_k((q/8) k^T  masked) v ; causal: key <= query.  io_type fp16/bf16; out_type fp16/bf16/fp32

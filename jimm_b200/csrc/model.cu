@@ -349,6 +349,31 @@ struct Packer {
     JIMM_TRY(upload_bias_at(attn_prefix + ".out.bias", {D}, lw->b, D));
     return 0;
   }
+  // MultiHeadAttentionPoolingHead parameters (common/vit.py:27-85) under `mp`
+  int map_head(const std::string& mp, int D, int H, VisionTower* v) {
+    const int d = D / H;
+    JIMM_TRY(fused_proj(mp + "attn", {"key", "value"}, D, H, &v->map_kv));
+    JIMM_TRY(out_proj(mp + "attn", D, H, &v->map_out));
+    JIMM_TRY(upload_ln(mp + "layernorm", D, &v->map_ln));
+    JIMM_TRY(linear(mp + "mlp.layers.0", D, 4 * D, true, &v->map_fc1));  // intermediate_size = 4*hidden (common/vit.py:175)
+    JIMM_TRY(linear(mp + "mlp.layers.2", 4 * D, D, true, &v->map_fc2));
+    // probe query is input independent: q = probe . Wq + bq  (common/vit.py:96-97), done once on the host in fp64
+    HostParam* probe = find(mp + "probe", {1, 1, D});
+    HostParam* wq = find(mp + "attn.query.kernel", {D, H, d});
+    HostParam* bq = find(mp + "attn.query.bias", {H, d});
+    if (!probe || !wq || !bq) return JIMM_ESTATE;
+    std::vector<float> q(D);
+    for (int o = 0; o < D; ++o) {
+      double acc = bq->data[o];
+      for (int i = 0; i < D; ++i) acc += static_cast<double>(probe->data[i]) * wq->data[static_cast<size_t>(i) * D + o];
+      q[o] = static_cast<float>(acc);
+    }
+    void* dq = nullptr;
+    JIMM_TRY(m->pool.alloc(&dq, D * sizeof(float)));
+    JIMM_CUDA_CHECK(cudaMemcpy(dq, q.data(), D * sizeof(float), cudaMemcpyHostToDevice));
+    v->map_q = static_cast<float*>(dq);
+    return 0;
+  }
   int encoder(const std::string& prefix, Encoder* enc) {
     const EncoderCfg& c = enc->c;
     enc->blocks.resize(c.L);
@@ -424,6 +449,19 @@ static int plan_encoder(jimm_model* m, Encoder* enc, int Tmax, EncBufs ws) {
   return 0;
 }
 
+static int plan_map_head(jimm_model* m, int Bm, int Tv) {
+  VisionTower& v = m->vis;
+  Workspace& ws = m->ws;
+  const int D = v.D;
+  JIMM_TRY(gemm_plan_init(&v.p_map_kv, m->cdt, ws.h, D, v.map_kv.w, D, Tv, 2 * D, D, epi_plain(v.map_kv, ACT_NONE, ws.big, m->adt, 2 * D, m->epi_mode_16)));
+  JIMM_TRY(gemm_plan_init(&v.p_map_out, m->cdt, ws.pooled, D, v.map_out.w, D, Bm, D, D, epi_plain(v.map_out, ACT_NONE, ws.feat, DT_F32, D, 0)));
+  JIMM_TRY(gemm_plan_init(&v.p_map_fc1, m->cdt, ws.pooled, D, v.map_fc1.w, D, Bm, 4 * D, D, epi_plain(v.map_fc1, ACT_GELU_TANH, ws.mid2, m->cdt, 4 * D, 0)));
+  GemmEpilogue e = epi_plain(v.map_fc2, ACT_NONE, ws.out_dev, DT_F32, D, 0);
+  e.residual = ws.feat; e.ldr = D;
+  JIMM_TRY(gemm_plan_init(&v.p_map_fc2, m->cdt, ws.mid2, 4 * D, v.map_fc2.w, 4 * D, Bm, D, 4 * D, e));
+  return 0;
+}
+
 // x: fp32 [B*S, D] residual stream in ws.x.  TransformerEncoder.__call__ x L (common/transformer.py:116-132,190-196).
 static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s, EncBufs ws) {
   const EncoderCfg& c = enc->c;
@@ -442,6 +480,21 @@ static int run_encoder(jimm_model* m, Encoder* enc, int B, int S, cudaStream_t s
     JIMM_TRY(run_gemm(m, b.p_fc2, ws.big, c.M, b.fc2, T, s, flip()));
   }
   return 0;
+}
+
+// MultiHeadAttentionPoolingHead.__call__ (common/vit.py:87-101) on the tokens in ws.h (compute dtype, [B*S, D]); out fp32 [B, D]
+static int run_map_head(jimm_model* m, int B, int S, float* out, cudaStream_t s) {
+  VisionTower& v = m->vis;
+  Workspace& ws = m->ws;
+  const int D = v.D, T = B * S;
+  JIMM_TRY(run_gemm(m, v.p_map_kv, ws.h, D, v.map_kv, T, s));                                        // k | v  [T, 2D]
+  JIMM_TRY(map_attention_run(v.map_q, ws.big, m->adt, ws.pooled, m->cdt, B, S, v.enc.c.H, s));     // [B, D]
+  JIMM_TRY(run_gemm(m, v.p_map_out, ws.pooled, D, v.map_out, B, s));                                 // -> feat fp32 [B, D]
+  JIMM_TRY(layernorm_run(ws.feat, D, 1, 0, nullptr, v.map_ln.scale, v.map_ln.bias, v.eps_outer, ws.pooled, m->cdt, D, B, D, s));
+  JIMM_TRY(run_gemm(m, v.p_map_fc1, ws.pooled, D, v.map_fc1, B, s));                                 // gelu -> mid2 [B, 4D]
+  GemmPlan p = v.p_map_fc2;  // + bias + residual(feat) -> out fp32 [B, D]
+  p.epi.out = out;
+  return run_gemm(m, p, ws.mid2, 4 * D, v.map_fc2, B, s);
 }
 
 // VisionTransformerBase.__call__ (common/vit.py:216-248) + the model's head.  out: fp32 [B, out_dim]
@@ -476,17 +529,7 @@ static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float
   // MAP head (common/vit.py:87-101)
   const int T = B * S;
   JIMM_TRY(layernorm_run(ws.x, D, 1, 0, nullptr, v.ln_post.scale, v.ln_post.bias, v.eps_outer, ws.h, m->cdt, D, T, D, s));
-  JIMM_TRY(run_gemm(m, v.p_map_kv, ws.h, D, v.map_kv, T, s));                                        // k | v  [T, 2D]
-  JIMM_TRY(map_attention_run(v.map_q, ws.big, m->adt, ws.pooled, m->cdt, B, S, v.enc.c.H, s));     // [B, D]
-  JIMM_TRY(run_gemm(m, v.p_map_out, ws.pooled, D, v.map_out, B, s));                                 // -> feat fp32 [B, D]
-  JIMM_TRY(layernorm_run(ws.feat, D, 1, 0, nullptr, v.map_ln.scale, v.map_ln.bias, v.eps_outer, ws.pooled, m->cdt, D, B, D, s));
-  JIMM_TRY(run_gemm(m, v.p_map_fc1, ws.pooled, D, v.map_fc1, B, s));                                 // gelu -> mid2 [B, 4D]
-  {
-    GemmPlan p = v.p_map_fc2;  // + bias + residual(feat) -> out fp32 [B, D]
-    p.epi.out = out;
-    JIMM_TRY(run_gemm(m, p, ws.mid2, 4 * D, v.map_fc2, B, s));
-  }
-  return 0;
+  return run_map_head(m, B, S, out, s);
 }
 
 // CLIP.encode_text (models/clip.py:148-167) / SigLIP.encode_text (models/siglip.py:135-153).  out fp32 [B, Dt]
@@ -604,6 +647,50 @@ static int exec_text(jimm_model* m, const int32_t* ids, int n, int T, float* out
   return 0;
 }
 
+// Handle of a bare sub-module (kind JIMM_ENCODER: Transformer, parameters "blocks.layers.{i}.*", common/transformer.py:135-196;
+// kind JIMM_MAPHEAD: MultiHeadAttentionPoolingHead, parameters "probe", "attn.*", "layernorm.*", "mlp.layers.{0,2}.*",
+// common/vit.py:12-101).  cfg: v_width / v_heads / v_mlp / v_layers / v_act / v_eps_block (block LN) / v_eps_outer (MAP LN) / t_causal,
+// ctx_len = max tokens per sample.  The same kernels and orchestration as inside a tower (run_encoder / run_map_head).
+static int finalize_sub(jimm_model* m, int max_batch) {
+  const jimm_config_t& c = m->cfg;
+  Packer pk{m};
+  int rc = 0;
+  VisionTower& v = m->vis;
+  v.present = false;
+  v.D = c.v_width; v.S = c.ctx_len; v.n = v.S; v.pooling = JIMM_POOL_MAP; v.eps_outer = c.v_eps_outer;
+  v.enc.c.D = c.v_width; v.enc.c.H = c.v_heads; v.enc.c.M = c.v_mlp; v.enc.c.L = c.kind == JIMM_ENCODER ? c.v_layers : 0;
+  v.enc.c.act = c.v_act; v.enc.c.causal = c.t_causal; v.enc.c.eps = c.v_eps_block;
+  const int D = v.D;
+  if (c.kind == JIMM_ENCODER) rc = pk.encoder("", &v.enc);
+  else rc = pk.map_head("", D, c.v_heads, &v);
+  pk.done();
+  if (rc) return rc;
+  for (auto& kv : m->host) {
+    if (!kv.second.used) { set_last_error("finalize: unexpected parameter '%s' was set but is not part of this module", kv.first.c_str()); return JIMM_ESTATE; }
+  }
+  m->host.clear();
+  Workspace& ws = m->ws;
+  const size_t cs = cdt_size(m), Bm = max_batch, Tv = Bm * v.S;
+  size_t big = Tv * 3 * D * 2;
+  if (Tv * static_cast<size_t>(c.v_mlp) * cs > big) big = Tv * static_cast<size_t>(c.v_mlp) * cs;
+  void* p = nullptr;
+  JIMM_TRY(m->pool.alloc(&p, Tv * D * sizeof(float))); ws.x = static_cast<float*>(p);
+  JIMM_TRY(m->pool.alloc(&ws.h, Tv * D * cs));
+  JIMM_TRY(m->pool.alloc(&ws.big, big));
+  JIMM_TRY(m->pool.alloc(&ws.pooled, Bm * D * cs));
+  JIMM_TRY(m->pool.alloc(&p, Bm * D * sizeof(float))); ws.feat = static_cast<float*>(p);
+  JIMM_TRY(m->pool.alloc(&ws.mid2, Bm * 4 * D * cs));
+  ws.out_dev_elems = Bm * D;
+  JIMM_TRY(m->pool.alloc(&p, ws.out_dev_elems * sizeof(float))); ws.out_dev = static_cast<float*>(p);
+  if (c.kind == JIMM_ENCODER) JIMM_TRY(plan_encoder(m, &v.enc, static_cast<int>(Tv), EncBufs{ws.x, ws.h, ws.big}));
+  else JIMM_TRY(plan_map_head(m, static_cast<int>(Bm), static_cast<int>(Tv)));
+  JIMM_CUDA_CHECK(cudaDeviceSynchronize());
+  m->graph_max_batch = 0;
+  m->max_batch = max_batch;
+  m->finalized = true;
+  return 0;
+}
+
 }  // namespace jimm
 
 // ==========================================================================================
@@ -618,7 +705,8 @@ long long jimm_graph_replay_count(void) { return g_graph_replays.load(); }
 
 int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) {
   if (!cfg || !out) { set_last_error("jimm_model_create: null argument"); return JIMM_EINVAL; }
-  if (cfg->kind < JIMM_VIT || cfg->kind > JIMM_TOWER) { set_last_error("bad kind %d", cfg->kind); return JIMM_EINVAL; }
+  if (cfg->kind < JIMM_VIT || cfg->kind > JIMM_MAPHEAD) { set_last_error("bad kind %d", cfg->kind); return JIMM_EINVAL; }
+  const bool sub = cfg->kind == JIMM_ENCODER || cfg->kind == JIMM_MAPHEAD;  // a bare Transformer / MultiHeadAttentionPoolingHead
   if (cfg->pooling != JIMM_POOL_CLS && cfg->pooling != JIMM_POOL_MAP) {
     set_last_error("pooling_type must be either MAP or CLS.");  // common/vit.py:178
     return JIMM_EINVAL;
@@ -633,7 +721,8 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
     return JIMM_EINVAL;
   }
   if (cfg->compute_dtype < JIMM_F32 || cfg->compute_dtype > JIMM_BF16) { set_last_error("bad compute_dtype"); return JIMM_EINVAL; }
-  if (cfg->patch <= 0 || cfg->img_size < cfg->patch || cfg->in_ch <= 0) {
+  if (sub && cfg->ctx_len <= 0) { set_last_error("sub-module handle: ctx_len (max tokens per sample) must be positive"); return JIMM_EINVAL; }
+  if (!sub && (cfg->patch <= 0 || cfg->img_size < cfg->patch || cfg->in_ch <= 0)) {
     set_last_error("unsupported patch/img/channels (%d/%d/%d)", cfg->patch, cfg->img_size, cfg->in_ch);
     return JIMM_EINVAL;
   }
@@ -712,6 +801,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   if (max_batch <= 0) { set_last_error("max_batch must be positive"); return JIMM_EINVAL; }
   JIMM_TRY(set_device(m));
   const jimm_config_t& c = m->cfg;
+  if (c.kind == JIMM_ENCODER || c.kind == JIMM_MAPHEAD) return finalize_sub(m, max_batch);
   const bool dual = c.kind == JIMM_CLIP || c.kind == JIMM_SIGLIP;
   const std::string vp = c.kind == JIMM_VIT ? "encoder." : (dual ? "vision_model." : "");
   Packer pk{m};
@@ -741,30 +831,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   if (c.pre_norm && (rc = pk.upload_ln(vp + "ln_pre", D, &v.ln_pre))) return fail(rc);
   if ((rc = pk.upload_ln(vp + "ln_post", D, &v.ln_post))) return fail(rc);
   if ((rc = pk.encoder(vp + "transformer.", &v.enc))) return fail(rc);
-  if (v.pooling == JIMM_POOL_MAP) {
-    const std::string mp = vp + "MAPHead.";
-    const int H = c.v_heads, d = D / H;
-    if ((rc = pk.fused_proj(mp + "attn", {"key", "value"}, D, H, &v.map_kv))) return fail(rc);
-    if ((rc = pk.out_proj(mp + "attn", D, H, &v.map_out))) return fail(rc);
-    if ((rc = pk.upload_ln(mp + "layernorm", D, &v.map_ln))) return fail(rc);
-    if ((rc = pk.linear(mp + "mlp.layers.0", D, 4 * D, true, &v.map_fc1))) return fail(rc);  // intermediate_size = 4*hidden (common/vit.py:175)
-    if ((rc = pk.linear(mp + "mlp.layers.2", 4 * D, D, true, &v.map_fc2))) return fail(rc);
-    // probe query is input independent: q = probe . Wq + bq  (common/vit.py:96-97), done once on the host in fp64
-    HostParam* probe = pk.find(mp + "probe", {1, 1, D});
-    HostParam* wq = pk.find(mp + "attn.query.kernel", {D, H, d});
-    HostParam* bq = pk.find(mp + "attn.query.bias", {H, d});
-    if (!probe || !wq || !bq) return fail(JIMM_ESTATE);
-    std::vector<float> q(D);
-    for (int o = 0; o < D; ++o) {
-      double acc = bq->data[o];
-      for (int i = 0; i < D; ++i) acc += static_cast<double>(probe->data[i]) * wq->data[static_cast<size_t>(i) * D + o];
-      q[o] = static_cast<float>(acc);
-    }
-    void* dq = nullptr;
-    if ((rc = m->pool.alloc(&dq, D * sizeof(float)))) return fail(rc);
-    cudaMemcpy(dq, q.data(), D * sizeof(float), cudaMemcpyHostToDevice);
-    v.map_q = static_cast<float*>(dq);
-  }
+  if (v.pooling == JIMM_POOL_MAP && (rc = pk.map_head(vp + "MAPHead.", D, c.v_heads, &v))) return fail(rc);
   if (c.kind == JIMM_VIT && c.num_classes > 0) {
     if ((rc = pk.linear("classifier", D, c.num_classes, true, &v.head))) return fail(rc);
   } else if (c.kind == JIMM_CLIP) {
@@ -860,17 +927,7 @@ int jimm_model_finalize(jimm_model_t* m, int max_batch) {
   if (v.head.N > 0)
     JIMM_TRY(gemm_plan_init(&v.p_head, m->cdt, ws.pooled, D, v.head.w, D, static_cast<int>(Bm), v.head.N, D,
                             epi_plain(v.head, ACT_NONE, ws.out_dev, DT_F32, v.head.N, 0)));
-  if (v.pooling == JIMM_POOL_MAP) {
-    JIMM_TRY(gemm_plan_init(&v.p_map_kv, m->cdt, ws.h, D, v.map_kv.w, D, static_cast<int>(Tv), 2 * D, D,
-                            epi_plain(v.map_kv, ACT_NONE, ws.big, m->adt, 2 * D, m->epi_mode_16)));
-    JIMM_TRY(gemm_plan_init(&v.p_map_out, m->cdt, ws.pooled, D, v.map_out.w, D, static_cast<int>(Bm), D, D,
-                            epi_plain(v.map_out, ACT_NONE, ws.feat, DT_F32, D, 0)));
-    JIMM_TRY(gemm_plan_init(&v.p_map_fc1, m->cdt, ws.pooled, D, v.map_fc1.w, D, static_cast<int>(Bm), 4 * D, D,
-                            epi_plain(v.map_fc1, ACT_GELU_TANH, ws.mid2, m->cdt, 4 * D, 0)));
-    GemmEpilogue e = epi_plain(v.map_fc2, ACT_NONE, ws.out_dev, DT_F32, D, 0);
-    e.residual = ws.feat; e.ldr = D;
-    JIMM_TRY(gemm_plan_init(&v.p_map_fc2, m->cdt, ws.mid2, 4 * D, v.map_fc2.w, 4 * D, static_cast<int>(Bm), D, 4 * D, e));
-  }
+  if (v.pooling == JIMM_POOL_MAP) JIMM_TRY(plan_map_head(m, static_cast<int>(Bm), static_cast<int>(Tv)));
   if (dual) {
     JIMM_TRY(plan_encoder(m, &t.enc, static_cast<int>(Bm) * t.T, EncBufs{m->wt.x, m->wt.h, m->wt.big}));
     JIMM_TRY(gemm_plan_init(&t.p_head, m->cdt, m->wt.pooled, t.D, t.head.w, t.D, static_cast<int>(Bm), t.D, t.D,
@@ -1012,6 +1069,40 @@ int jimm_dual_forward(jimm_model_t* m, const void* img, int in_dtype, int Bi, co
   return jimm_contrastive_logits(m, m->ws.emb_i, Bi, m->ws.emb_t, Bt, logits, stream);
 }
 
+// ---- forward of a bare sub-module (device buffers) ----
+static int check_sub(jimm_model_t* m, int kind, int B, int S, const void* x, const void* out) {
+  JIMM_TRY(check_ready(m, B));
+  if (m->cfg.kind != kind) { set_last_error("this handle is not a %s", kind == JIMM_ENCODER ? "Transformer (JIMM_ENCODER)" : "MAP head (JIMM_MAPHEAD)"); return JIMM_EINVAL; }
+  if (S <= 0 || S > m->vis.S) { set_last_error("sequence length %d outside (0, %d]", S, m->vis.S); return JIMM_EINVAL; }
+  if (!x || !out) { set_last_error("null buffer"); return JIMM_EINVAL; }
+  return set_device(m);
+}
+
+int jimm_encoder_forward(jimm_model_t* m, const float* x, int B, int S, float* out, void* stream) {
+  JIMM_TRY(check_sub(m, JIMM_ENCODER, B, S, x, out));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t row = static_cast<size_t>(S) * m->vis.D;
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(m->ws.x, x + b0 * row, nb * row * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    JIMM_TRY(run_encoder(m, &m->vis.enc, nb, S, s, EncBufs{m->ws.x, m->ws.h, m->ws.big}));
+    JIMM_CUDA_CHECK(cudaMemcpyAsync(out + b0 * row, m->ws.x, nb * row * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+int jimm_map_head_forward(jimm_model_t* m, const float* x, int B, int S, float* out, void* stream) {
+  JIMM_TRY(check_sub(m, JIMM_MAPHEAD, B, S, x, out));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t row = static_cast<size_t>(S) * m->vis.D;
+  for (int b0 = 0; b0 < B; b0 += m->max_batch) {
+    const int nb = B - b0 < m->max_batch ? B - b0 : m->max_batch;
+    JIMM_TRY(cast_run(x + b0 * row, m->ws.h, m->cdt, nb * row, s));  // the head's inputs are GEMM operands: compute dtype
+    JIMM_TRY(run_map_head(m, nb, S, out + static_cast<size_t>(b0) * m->vis.D, s));
+  }
+  return 0;
+}
+
 // ---- forward, host buffers ----
 static int ensure_copy_stream(jimm_model* m) {
   if (m->copy_stream) return 0;
@@ -1128,9 +1219,12 @@ static int vit_forward_host_impl(jimm_model_t* m, const void* img_host, int in_d
       JIMM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_copied[slot], 0));
       if (pre) {
         if (int rc = jimm_preproc_run(pre, copy_dst, n, Hin, Win, img_dst, tower_dtype, s)) return rc;
+        // the byte staging slice is free as soon as the front-end has read it: the next call's copy runs under THIS call's tower
+        // (the front-end's output slice is only rewritten by the next call's front-end, which is stream-ordered after this tower)
+        JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       }
       JIMM_TRY(exec_vision(m, img_dst, tower_dtype, n, out_d, s));
-      JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
+      if (!pre) JIMM_CUDA_CHECK(cudaEventRecord(m->ev_consumed[slot], s));
       m->slot_recorded[slot] = true;
       off += n;
     }
@@ -1295,6 +1389,10 @@ int jimm_k_map_attention(const float* q, const void* kv, int io_type, void* out,
 }
 int jimm_k_patchify(const void* img, int in_type, int B, int H, int W, int C, int P, void* out, int out_type, void* stream) {
   return patchify_run(img, in_type, B, H, W, C, P, out, out_type, static_cast<cudaStream_t>(stream));
+}
+int jimm_k_activation(const float* x, float* y, long long n, int act, void* stream) {
+  if (n < 0 || (n > 0 && (!x || !y))) { set_last_error("jimm_k_activation: bad arguments"); return JIMM_EINVAL; }
+  return activation_run(x, y, static_cast<size_t>(n), act, static_cast<cudaStream_t>(stream));
 }
 int jimm_k_embed(const int32_t* ids, const float* table, const float* pos, float* x, int B, int T, int D, int vocab, void* stream) {
   return embed_run(ids, table, pos, x, B, T, D, vocab, static_cast<cudaStream_t>(stream));

@@ -341,6 +341,62 @@ def test_dual_tower_medium(kind):
         check_parity(case, "text_embeds T=11", torch.float16, "fp32", m.encode_text(txt[:, :11].cuda()), ref_s, TOL)
 
 
+# ------------------------------------------------------------------ bare sub-modules (common/transformer.py, common/vit.py)
+@pytest.mark.parametrize("causal,quick", [(False, False), (True, True)])
+def test_transformer_and_encoder_call(causal, quick):
+    """Transformer.__call__ / TransformerEncoder.__call__ on their own (common/transformer.py:116-132,190-196): [B,S,D] -> [B,S,D]
+    through jimm_encoder_forward, against the oracle's block stack; the causal mask is the reference's tril(ones(T,T)) sliced to S."""
+    from jimm_b200.common.transformer import Transformer, TransformerEncoder, quickgelu
+
+    D, M, H, L, T = 128, 512, 2, 3, 20
+    g = torch.Generator().manual_seed(41)
+    p = {}
+    O._rand_blocks(p, g, "", L, D, H, M)
+    p = O.cast_params(p, torch.float32)
+    mask = torch.tril(torch.ones(T, T)) if causal else None
+    x = torch.randn(5, 13, D, generator=g)
+    with torch.no_grad():
+        ref = O.transformer(p, "", x, L, H, quick, mask, 1e-5)
+        ref1 = O.transformer_encoder(p, "blocks.layers.1.", x, H, 1e-5, quick, mask)
+    for dtype in (torch.float16, torch.float32):
+        t = _set(Transformer(D, M, L, H, layernorm_epsilon=1e-5, attn_mask=mask, use_quick_gelu=quick, dtype=dtype), p)
+        out = t(x.cuda())
+        assert out.shape == x.shape and out.is_cuda
+        check_parity(f"bare Transformer 3x128 causal={causal}", "activations", dtype, "fp32", out, ref, TOL)
+        assert torch.equal(t(x), out.cpu())  # host in -> host out
+        e = TransformerEncoder(D, M, H, layernorm_epsilon=1e-5, attn_mask=mask, use_quick_gelu=quick, dtype=dtype)
+        for k, v in p.items():
+            if k.startswith("blocks.layers.1."):
+                e.set_flat_param(k[len("blocks.layers.1."):], v)
+        check_parity(f"bare TransformerEncoder 128 causal={causal}", "activations", dtype, "fp32", e(x.cuda()), ref1, TOL)
+    # longer sequences rebuild the handle; an arbitrary mask is refused
+    x2 = torch.randn(2, 40 if not causal else 20, D, generator=g)
+    with torch.no_grad():
+        ref2 = O.transformer(p, "", x2, L, H, quick, mask, 1e-5)
+    check_parity(f"bare Transformer 3x128 causal={causal}", "activations (longer seq)", torch.float32, "fp32", t(x2.cuda()), ref2, TOL)
+    with pytest.raises(NotImplementedError):
+        Transformer(D, M, 1, H, attn_mask=torch.ones(T, T))(x.cuda())
+    y = torch.randn(1000, generator=g)
+    assert float((quickgelu(y.cuda()).cpu() - O.quickgelu(y)).abs().max()) < 1e-6
+
+
+def test_map_head_call():
+    """MultiHeadAttentionPoolingHead.__call__ on its own (common/vit.py:87-101): [B,S,D] -> [B,D]."""
+    from jimm_b200.common.vit import MultiHeadAttentionPoolingHead
+
+    D, H = 128, 2
+    t = O.TowerCfg(32, 8, 3, D, 0, H, 4 * D, "MAP", layernorm_epsilon=1e-6)
+    p = {k[len("MAPHead."):]: v for k, v in O.random_tower_params(t, seed=43).items() if k.startswith("MAPHead.")}
+    x = torch.randn(6, 16, D, generator=torch.Generator().manual_seed(44))
+    with torch.no_grad():
+        ref = O.map_head(p, "", x, H, 1e-6)
+    for dtype in (torch.float16, torch.float32):
+        h = _set(MultiHeadAttentionPoolingHead(D, 4 * D, H, 1e-6, dtype=dtype), p)
+        out = h(x.cuda())
+        assert out.shape == (6, D)
+        check_parity("bare MAP head 128", "pooled", dtype, "fp32", out, ref, TOL)
+
+
 def test_finalize_strictness():
     """Missing / unexpected / mis-shaped parameters are rejected by name (models/vit.py:229-232,259-268)."""
     import ctypes as C
