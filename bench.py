@@ -425,9 +425,8 @@ def collective_leg(args, rank, world, local, lib):
     _lib_check = __import__("jimm_b200._lib", fromlist=["check"]).check
     _lib_check(lib.jimm_k_l2_normalize(vp(ie_rows), vp(ni), E, B, E, st))
     _lib_check(lib.jimm_k_l2_normalize(vp(te_all), vp(nt), E, world * B, E, st))
-    fp = m.flat_params()
-    scale = fp["logit_scale"].to(bw.dev).reshape(1).contiguous()
-    bias = fp["logit_bias"].to(bw.dev).reshape(1).contiguous() if "logit_bias" in fp else None
+    scale = m.logit_scale.to(bw.dev).reshape(1).contiguous()
+    bias = m.logit_bias.to(bw.dev).reshape(1).contiguous() if "logit_bias" in m._params else None
     single = torch.empty((B, world * B), dtype=torch.float32, device=bw.dev)
     _lib_check(lib.jimm_k_logits(vp(ni), vp(nt), vp(scale), vp(bias) if bias is not None else None, vp(single), B, world * B, E, world * B, st))
     same = torch.tensor([int(torch.equal(single, lg))], device=bw.dev)

@@ -74,6 +74,15 @@ JIMM_API int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_
  * (e.g. "encoder.transformer.blocks.layers.0.attn.query.kernel", shape (D,H,d)).
  * `host` is read during the call.  dtype: JIMM_F32 | JIMM_F16 | JIMM_BF16. */
 JIMM_API int jimm_model_set_param(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype);
+/* Zero-copy hand-off: `host` is BORROWED and must stay valid and unchanged until jimm_model_finalize returns (e.g. the mmap of a
+ * safetensors file).  `shape` is still the reference's flax shape.  flags & JIMM_PARAM_TRANSPOSED: the memory holds the 2-D transpose
+ * [N, K] of the flax kernel's (K, N) view -- a HuggingFace (out, in) weight exactly as stored in the checkpoint, i.e. the transform
+ * `W.T.reshape(...)` of models/vit.py:241-250 is NOT applied by the caller; that is already the K-major operand layout of the GEMMs,
+ * so finalize only casts it.  Casts, transposes and packing run on the GPU; bytes go through a pinned staging ring; finalize
+ * synchronises once. */
+enum jimm_param_flags { JIMM_PARAM_TRANSPOSED = 1 };
+JIMM_API int jimm_model_set_param_ref(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype,
+                                      int flags);
 /* Pack weights (fused [3D,D] QKV, K-major operands, dtype cast), build TMA descriptors, size the workspace for
  * `max_batch` samples per call.  Fails (JIMM_ESTATE) naming the first missing / unexpected / mis-shaped parameter --
  * the analogue of the reference's strict visit checks (models/vit.py:229-232,259-268). */

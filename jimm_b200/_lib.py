@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjimm_b200.so")
 
 F32, F16, BF16, I32 = 0, 1, 2, 3
+PARAM_TRANSPOSED = 1
 KIND_VIT, KIND_CLIP, KIND_SIGLIP, KIND_TOWER, KIND_ENCODER, KIND_MAPHEAD = 0, 1, 2, 3, 4, 5
 POOL_CLS, POOL_MAP = 0, 1
 ACT_GELU_TANH, ACT_QUICK_GELU = 0, 1
@@ -54,6 +55,7 @@ SIGNATURES = {
     "jimm_graph_replay_count": (C.c_longlong, []),
     "jimm_model_create": (_i, [C.POINTER(Config), _i, C.POINTER(_vp)]),
     "jimm_model_set_param": (_i, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _i, _i]),
+    "jimm_model_set_param_ref": (_i, [_vp, C.c_char_p, _vp, C.POINTER(C.c_int64), _i, _i, _i]),
     "jimm_model_finalize": (_i, [_vp, _i]),
     "jimm_model_destroy": (_i, [_vp]),
     "jimm_model_output_dim": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .nn import LazyParam
 
 _TORCH_TO_CODE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
@@ -58,14 +59,22 @@ class NativeModel:
         self.handle = C.c_void_p()
         _lib.check(self.lib.jimm_model_create(C.byref(cfg), self.device_index, C.byref(self.handle)))
         try:
+            keep = []  # the borrowed buffers stay alive until finalize has streamed them to the GPU
             for name, t in params.items():
+                flags = 0
+                if isinstance(t, LazyParam):  # a view of checkpoint memory, possibly the (out, in) transpose of the flax kernel
+                    shape_t, flags, t = t.shape, (_lib.PARAM_TRANSPOSED if t.transposed else 0), t.base
+                else:
+                    shape_t = tuple(t.shape)
                 t = t.detach()
                 if t.dtype not in _TORCH_TO_CODE:
                     t = t.to(torch.float32)
-                t = t.contiguous().cpu()
-                shape = (C.c_int64 * max(t.ndim, 1))(*t.shape)
-                _lib.check(self.lib.jimm_model_set_param(self.handle, name.encode(), C.c_void_p(t.data_ptr()), shape, t.ndim,
-                                                          _TORCH_TO_CODE[t.dtype]))
+                if t.is_cuda or not t.is_contiguous():
+                    t = t.contiguous().cpu()
+                keep.append(t)
+                shape = (C.c_int64 * max(len(shape_t), 1))(*shape_t)
+                _lib.check(self.lib.jimm_model_set_param_ref(self.handle, name.encode(), C.c_void_p(t.data_ptr()), shape, len(shape_t),
+                                                              _TORCH_TO_CODE[t.dtype], flags))
             _lib.check(self.lib.jimm_model_finalize(self.handle, int(max_batch)))
         except Exception:
             self.lib.jimm_model_destroy(self.handle)

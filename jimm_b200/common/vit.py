@@ -77,7 +77,7 @@ class _NativeOwner:
         if n is not None:
             n.close()
         mb = max(self._max_batch, int(batch) if require else 1)
-        n = NativeModel(self._native_config(), self.flat_params(), mb)
+        n = NativeModel(self._native_config(), self.flat_params(raw=True), mb)
         n.preproc = self._preproc
         object.__setattr__(self, "_native", n)
         return n

@@ -45,6 +45,26 @@ int logits_run(const float* img, const float* txt, const float* logit_scale, con
 // dst[n*K + k] = cast(src[k*N + n])   (flax (in,out) kernel -> K-major [N,K] operand)
 int transpose_cast_run(const float* src, int K, int N, void* dst, int out_type, int ldd, cudaStream_t stream);
 int cast_run(const float* src, void* dst, int out_type, size_t n, cudaStream_t stream);
+
+// ---- checkpoint ingestion (pack.cu) ----
+// rows of K elements of src_type (DT_F32 | DT_F16 | DT_BF16), row-major -> dst[r * ldd + k] of out_type
+int pack_rows_run(const void* src, int src_type, size_t rows, size_t K, void* dst, int out_type, size_t ldd, cudaStream_t stream);
+// kc rows (starting at row k0) of a (K, N) row-major matrix of src_type -> dst[n * ldd + k0 + k] of out_type (K-major operand)
+int pack_transpose_run(const void* src, int src_type, int kc, int N, void* dst, int out_type, size_t ldd, int k0, cudaStream_t stream);
+// two pinned host slots + two device slots: memcpy of chunk i+1 overlaps the DMA and the pack kernel of chunk i
+struct UploadRing {
+  static constexpr size_t kCap = static_cast<size_t>(32) << 20;
+  void* pinned[2] = {nullptr, nullptr};
+  void* dev[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool busy[2] = {false, false};
+  int cur = 0;
+  bool ready = false;
+  int init();
+  void destroy();
+  int stage(const void* src, size_t bytes, cudaStream_t s, void** dptr);  // host -> pinned slot -> device slot (async); *dptr = device slot
+  int commit(cudaStream_t s);                                              // after the consuming kernel has been enqueued
+};
 int activation_run(const float* x, float* y, size_t n, int act /* 0 none, 1 gelu_tanh, 2 quick_gelu */, cudaStream_t stream);
 
 // Multi-head softmax attention over the fused qkv buffer [B*S, 3D] (q | k | v, heads of 64).  SURVEY 8a row a5.

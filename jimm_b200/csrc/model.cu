@@ -79,10 +79,22 @@ struct DevPool {
 };
 
 struct HostParam {
-  std::vector<int64_t> shape;
-  std::vector<float> data;
+  std::vector<int64_t> shape;   // the reference's flax shape
+  std::vector<float> data;      // owned fp32 copy (jimm_model_set_param) ...
+  const void* ref = nullptr;    // ... or a borrowed host pointer (jimm_model_set_param_ref), valid until finalize returns
+  int dtype = DT_F32;           // element type behind ptr()
+  bool transposed = false;      // ref holds the 2-D transpose [N, K] of the flax kernel's (K, N) view (a HuggingFace (out, in) weight as is)
   bool used = false;
-  size_t numel() const { return data.size(); }
+  size_t n = 0;
+  size_t numel() const { return n; }
+  const void* ptr() const { return ref ? ref : static_cast<const void*>(data.data()); }
+  size_t esize() const { return dtype == DT_F32 ? 4 : 2; }
+  float at(size_t i) const {  // host-side read of element i of the STORED order
+    if (dtype == DT_F32) return static_cast<const float*>(ptr())[i];
+    const uint16_t h = static_cast<const uint16_t*>(ptr())[i];
+    if (dtype == DT_BF16) { uint32_t u = static_cast<uint32_t>(h) << 16; float f; memcpy(&f, &u, 4); return f; }
+    return __half2float(*reinterpret_cast<const __half*>(&h));
+  }
 };
 
 struct LinearW {
@@ -242,20 +254,13 @@ static size_t cdt_size(const jimm_model* m) { return dtype_size(m->cdt); }
 // ------------------------------------------------------------------------------------------
 struct Packer {
   jimm_model* m;
-  float* stage = nullptr;  // fp32 device staging buffer
-  size_t stage_elems = 0;
+  UploadRing ring;
   cudaStream_t stream = 0;
 
-  int ensure_stage(size_t n) {
-    if (n <= stage_elems) return 0;
-    if (stage) { cudaStreamSynchronize(stream); cudaFree(stage); stage = nullptr; }
-    cudaError_t e = cudaMalloc(&stage, n * sizeof(float));
-    if (e != cudaSuccess) { set_last_error("cudaMalloc staging (%zu floats) failed: %s", n, cudaGetErrorString(e)); return JIMM_ENOMEM; }
-    stage_elems = n;
-    return 0;
-  }
+  // one synchronisation for the whole finalize
   void done() {
-    if (stage) { cudaStreamSynchronize(stream); cudaFree(stage); stage = nullptr; stage_elems = 0; }
+    cudaStreamSynchronize(stream);
+    ring.destroy();
   }
 
   HostParam* find(const std::string& name, std::initializer_list<int64_t> shape) {
@@ -277,14 +282,46 @@ struct Packer {
     return &hp;
   }
 
-  // fp32 vector/tensor uploaded as is
+  // `rows` rows of K stored elements -> dst[r * ldd + k] of out_type, streamed through the ring in row chunks
+  int rows_to_device(const HostParam* hp, size_t rows, size_t K, void* dst, int out_type, size_t ldd) {
+    const size_t es = hp->esize(), row_bytes = K * es;
+    if (row_bytes == 0 || rows == 0) return 0;
+    const uint8_t* src = static_cast<const uint8_t*>(hp->ptr());
+    const size_t out_es = dtype_size(out_type);
+    if (row_bytes > UploadRing::kCap) {  // a single very long row (flat vectors): split it into pieces
+      if (rows != 1 || ldd != K) { set_last_error("finalize: row of %zu bytes exceeds the staging slot", row_bytes); return JIMM_EINVAL; }
+      const size_t per = UploadRing::kCap / es;
+      for (size_t k0 = 0; k0 < K; k0 += per) {
+        const size_t kc = K - k0 < per ? K - k0 : per;
+        void* d = nullptr;
+        JIMM_TRY(ring.stage(src + k0 * es, kc * es, stream, &d));
+        JIMM_TRY(pack_rows_run(d, hp->dtype, 1, kc, static_cast<uint8_t*>(dst) + k0 * out_es, out_type, kc, stream));
+        JIMM_TRY(ring.commit(stream));
+      }
+      return 0;
+    }
+    const size_t per = UploadRing::kCap / row_bytes;
+    for (size_t r0 = 0; r0 < rows; r0 += per) {
+      const size_t rc = rows - r0 < per ? rows - r0 : per;
+      void* d = nullptr;
+      JIMM_TRY(ring.stage(src + r0 * row_bytes, rc * row_bytes, stream, &d));
+      JIMM_TRY(pack_rows_run(d, hp->dtype, rc, K, static_cast<uint8_t*>(dst) + r0 * ldd * out_es, out_type, ldd, stream));
+      JIMM_TRY(ring.commit(stream));
+    }
+    return 0;
+  }
+
+  // fp32 vector / tensor uploaded element for element (biases, LayerNorm, cls, pos, embedding table, scalars)
   int upload_f32(const std::string& name, std::initializer_list<int64_t> shape, float** out) {
     HostParam* hp = find(name, shape);
     if (!hp) return JIMM_ESTATE;
+    if (hp->transposed) { set_last_error("finalize: '%s' cannot be handed over transposed", name.c_str()); return JIMM_EINVAL; }
     void* d = nullptr;
     JIMM_TRY(m->pool.alloc(&d, hp->numel() * sizeof(float)));
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(d, hp->data.data(), hp->numel() * sizeof(float), cudaMemcpyHostToDevice, stream));
-    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // 2-D tensors go row by row so that a long table streams through the ring in row chunks
+    const size_t K = hp->shape.empty() ? 1 : static_cast<size_t>(hp->shape.back());
+    const size_t rows = K ? hp->numel() / K : 0;
+    JIMM_TRY(rows_to_device(hp, rows, K, d, DT_F32, K));
     *out = static_cast<float*>(d);
     return 0;
   }
@@ -293,17 +330,25 @@ struct Packer {
     JIMM_TRY(upload_f32(prefix + ".bias", {D}, &ln->bias));
     return 0;
   }
-  // flax kernel viewed as (K, N) row-major  ->  rows [n0, n0+N) of a packed [Ntot, K] K-major operand
+  // flax kernel viewed as (K, N) row-major  ->  rows [n0, n0+N) of a packed [Ntot, ldd] K-major operand (ldd >= K: zero-padded K)
   int pack_kernel(const std::string& name, std::initializer_list<int64_t> shape, int K, int N, void* dst_base, int n0, int ldd = 0) {
     if (ldd <= 0) ldd = K;
     HostParam* hp = find(name, shape);
     if (!hp) return JIMM_ESTATE;
     if (hp->numel() != static_cast<size_t>(K) * N) { set_last_error("finalize: '%s' numel mismatch", name.c_str()); return JIMM_ESTATE; }
-    JIMM_TRY(ensure_stage(hp->numel()));
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(stage, hp->data.data(), hp->numel() * sizeof(float), cudaMemcpyHostToDevice, stream));
     uint8_t* dst = static_cast<uint8_t*>(dst_base) + static_cast<size_t>(n0) * ldd * cdt_size(m);
-    JIMM_TRY(transpose_cast_run(stage, K, N, dst, m->cdt, ldd, stream));
-    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (hp->transposed) return rows_to_device(hp, N, K, dst, m->cdt, ldd);  // already [N, K]: cast-copy
+    const size_t es = hp->esize(), row_bytes = static_cast<size_t>(N) * es;
+    if (row_bytes > UploadRing::kCap) { set_last_error("finalize: '%s' row of %zu bytes exceeds the staging slot", name.c_str(), row_bytes); return JIMM_EINVAL; }
+    const int per = static_cast<int>(UploadRing::kCap / row_bytes);
+    const uint8_t* src = static_cast<const uint8_t*>(hp->ptr());
+    for (int k0 = 0; k0 < K; k0 += per) {
+      const int kc = K - k0 < per ? K - k0 : per;
+      void* d = nullptr;
+      JIMM_TRY(ring.stage(src + static_cast<size_t>(k0) * row_bytes, static_cast<size_t>(kc) * row_bytes, stream, &d));
+      JIMM_TRY(pack_transpose_run(d, hp->dtype, kc, N, dst, m->cdt, ldd, k0, stream));
+      JIMM_TRY(ring.commit(stream));
+    }
     return 0;
   }
   int alloc_linear(LinearW* lw, int N, int K, bool bias) {
@@ -320,10 +365,10 @@ struct Packer {
     HostParam* hp = find(name, shape);
     if (!hp) return JIMM_ESTATE;
     if (hp->numel() != count) { set_last_error("finalize: '%s' numel mismatch", name.c_str()); return JIMM_ESTATE; }
-    JIMM_CUDA_CHECK(cudaMemcpyAsync(dst, hp->data.data(), count * sizeof(float), cudaMemcpyHostToDevice, stream));
-    JIMM_CUDA_CHECK(cudaStreamSynchronize(stream));
-    return 0;
+    return rows_to_device(hp, 1, count, dst, DT_F32, count);
   }
+  // element (k, n) of a kernel's flax (K, N) view, whatever its stored order
+  static float kn(const HostParam* hp, size_t k, size_t n, size_t K, size_t N) { return hp->transposed ? hp->at(n * K + k) : hp->at(k * N + n); }
   // nnx.Linear: kernel (K,N), optional bias (N)
   int linear(const std::string& prefix, int K, int N, bool bias, LinearW* lw) {
     JIMM_TRY(alloc_linear(lw, N, K, bias));
@@ -364,8 +409,8 @@ struct Packer {
     if (!probe || !wq || !bq) return JIMM_ESTATE;
     std::vector<float> q(D);
     for (int o = 0; o < D; ++o) {
-      double acc = bq->data[o];
-      for (int i = 0; i < D; ++i) acc += static_cast<double>(probe->data[i]) * wq->data[static_cast<size_t>(i) * D + o];
+      double acc = bq->at(o);
+      for (int i = 0; i < D; ++i) acc += static_cast<double>(probe->at(i)) * kn(wq, i, o, D, D);
       q[o] = static_cast<float>(acc);
     }
     void* dq = nullptr;
@@ -765,32 +810,41 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   return 0;
 }
 
-int jimm_model_set_param(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype) {
-  if (!m || !flax_path || !host || (ndim > 0 && !shape)) { set_last_error("jimm_model_set_param: null argument"); return JIMM_EINVAL; }
-  if (m->finalized) { set_last_error("model already finalized"); return JIMM_ESTATE; }
-  HostParam hp;
+static int make_host_param(const int64_t* shape, int ndim, HostParam* hp) {
   size_t n = 1;
   for (int i = 0; i < ndim; ++i) {
     if (shape[i] < 0) { set_last_error("negative dim"); return JIMM_EINVAL; }
-    hp.shape.push_back(shape[i]);
+    hp->shape.push_back(shape[i]);
     n *= static_cast<size_t>(shape[i]);
   }
-  hp.data.resize(n);
-  if (dtype == JIMM_F32) {
-    memcpy(hp.data.data(), host, n * sizeof(float));
-  } else if (dtype == JIMM_F16) {
-    const __half* h = static_cast<const __half*>(host);
-    for (size_t i = 0; i < n; ++i) hp.data[i] = __half2float(h[i]);
-  } else if (dtype == JIMM_BF16) {
-    const uint16_t* h = static_cast<const uint16_t*>(host);
-    for (size_t i = 0; i < n; ++i) {
-      uint32_t u = static_cast<uint32_t>(h[i]) << 16;
-      memcpy(&hp.data[i], &u, 4);
-    }
-  } else {
-    set_last_error("set_param: unsupported dtype %d", dtype);
-    return JIMM_EINVAL;
-  }
+  hp->n = n;
+  return 0;
+}
+
+int jimm_model_set_param(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype) {
+  if (!m || !flax_path || !host || (ndim > 0 && !shape)) { set_last_error("jimm_model_set_param: null argument"); return JIMM_EINVAL; }
+  if (m->finalized) { set_last_error("model already finalized"); return JIMM_ESTATE; }
+  if (dtype < JIMM_F32 || dtype > JIMM_BF16) { set_last_error("set_param: unsupported dtype %d", dtype); return JIMM_EINVAL; }
+  HostParam hp;
+  JIMM_TRY(make_host_param(shape, ndim, &hp));
+  hp.dtype = dtype;  // kept in the caller's element type: the cast happens on the GPU at finalize
+  const size_t bytes = hp.n * hp.esize();
+  hp.data.resize((bytes + 3) / 4);
+  memcpy(hp.data.data(), host, bytes);
+  m->host[flax_path] = std::move(hp);
+  return 0;
+}
+
+int jimm_model_set_param_ref(jimm_model_t* m, const char* flax_path, const void* host, const int64_t* shape, int ndim, int dtype, int flags) {
+  if (!m || !flax_path || !host || (ndim > 0 && !shape)) { set_last_error("jimm_model_set_param_ref: null argument"); return JIMM_EINVAL; }
+  if (m->finalized) { set_last_error("model already finalized"); return JIMM_ESTATE; }
+  if (dtype < JIMM_F32 || dtype > JIMM_BF16) { set_last_error("set_param_ref: unsupported dtype %d", dtype); return JIMM_EINVAL; }
+  HostParam hp;
+  JIMM_TRY(make_host_param(shape, ndim, &hp));
+  hp.dtype = dtype;
+  hp.ref = host;
+  hp.transposed = (flags & JIMM_PARAM_TRANSPOSED) != 0;
+  if (hp.transposed && ndim < 2) { set_last_error("set_param_ref: '%s': only kernels (ndim >= 2) can be handed over transposed", flax_path); return JIMM_EINVAL; }
   m->host[flax_path] = std::move(hp);
   return 0;
 }

@@ -9,32 +9,6 @@ from ..common.transformer import Transformer, g_wrap
 from ..common.vit import _NativeOwner, tower_config_fields
 
 
-def hf_block_mapping(mapping: dict, flax_base: str, hf_base: str):
-    """The 16 per-layer (flax path -> HF name) pairs shared by CLIP and SigLIP (models/clip.py:291-334, models/siglip.py:263-306)."""
-    for fl, hf in (("query", "q_proj"), ("key", "k_proj"), ("value", "v_proj"), ("out", "out_proj")):
-        mapping[flax_base + f"attn.{fl}.kernel"] = hf_base + f"self_attn.{hf}.weight"
-        mapping[flax_base + f"attn.{fl}.bias"] = hf_base + f"self_attn.{hf}.bias"
-    for n, h in (("norm1", "layer_norm1"), ("norm2", "layer_norm2")):
-        mapping[flax_base + f"{n}.scale"] = hf_base + f"{h}.weight"
-        mapping[flax_base + f"{n}.bias"] = hf_base + f"{h}.bias"
-    for i, h in ((0, "fc1"), (3, "fc2")):
-        mapping[flax_base + f"mlp.layers.{i}.kernel"] = hf_base + f"mlp.{h}.weight"
-        mapping[flax_base + f"mlp.layers.{i}.bias"] = hf_base + f"mlp.{h}.bias"
-
-
-def transform_attn(v: torch.Tensor, hf_key: str, hidden: int, heads: int) -> torch.Tensor:
-    """q/k/v/out projection layout transforms (models/clip.py:362-390, models/siglip.py:324-351)."""
-    d = hidden // heads
-    last2 = hf_key.split(".")[-2:]
-    if last2[1] == "weight" and last2[0] in ("q_proj", "k_proj", "v_proj"):
-        return v.T.reshape(hidden, heads, d)
-    if last2[1] == "bias" and last2[0] in ("q_proj", "k_proj", "v_proj"):
-        return v.reshape(heads, d)
-    if last2 == ["out_proj", "weight"]:
-        return v.T.reshape(heads, d, hidden)
-    return v
-
-
 class DualTower(_NativeOwner, nn.Module):
     """Base of CLIP and SigLIP: holds the shared attributes and the encode / call plumbing."""
 
@@ -131,9 +105,8 @@ class DualTower(_NativeOwner, nn.Module):
         t_n = te / torch.linalg.norm(te, dim=-1, keepdim=True)
         gathered = torch.empty((world * B, t_n.shape[1]), dtype=torch.float32, device=n.device)
         dist.all_gather_into_tensor(gathered, t_n.contiguous())
-        fp = self.flat_params()
-        scale = fp["logit_scale"].to(n.device).reshape(1)
-        bias = fp["logit_bias"].to(n.device).reshape(1) if "logit_bias" in fp else None
+        scale = self.logit_scale.to(n.device).reshape(1)
+        bias = self.logit_bias.to(n.device).reshape(1) if "logit_bias" in self._params else None
         import ctypes as C
 
         out = torch.empty((B, world * B), dtype=torch.float32, device=n.device)

@@ -2,15 +2,14 @@
 
 from __future__ import annotations
 
-from typing import Any, Set
-
 import torch
 
 from .. import _lib, nn
 from ..common.transformer import g_wrap
+from ..common import hf_loader as L
 from ..common.utils import load_params_and_config
 from ..common.vit import VisionTransformerBase, tower_config_fields
-from ._dual import DualTower, build_text_tower, hf_block_mapping, transform_attn
+from ._dual import DualTower, build_text_tower
 
 
 class CLIP(DualTower):
@@ -44,88 +43,53 @@ class CLIP(DualTower):
     @classmethod
     def from_pretrained(cls, model_name_or_path: str, use_pytorch: bool = False, mesh=None, dtype=torch.float32) -> "CLIP":
         """Load a HF `CLIPModel` checkpoint (models/clip.py:190-416)."""
-        params_fstate, config = load_params_and_config(model_name_or_path, use_pytorch)
+        hf, config = load_params_and_config(model_name_or_path, use_pytorch)
         if config == {}:
-            if not use_pytorch:
-                tw = params_fstate["text_model.embeddings.token_embedding.weight"]
-                text_hidden, text_vocab = tw.shape[1], tw.shape[0]
-                text_ctx = params_fstate["text_model.embeddings.position_embedding.weight"].shape[0]
-                text_layers = 0
-                for k in params_fstate:
-                    if k.startswith("text_model.encoder.layers.") and k.endswith(".self_attn.q_proj.weight"):
-                        text_layers = max(text_layers, int(k.split(".")[3]) + 1)
-                vis_hidden = params_fstate["vision_model.embeddings.class_embedding"].shape[0]
-                vis_patch = params_fstate["vision_model.embeddings.patch_embedding.weight"].shape[2]
-                vis_img = int((params_fstate["vision_model.embeddings.position_embedding.weight"].shape[0] - 1) ** 0.5) * vis_patch
-                vis_layers = 0
-                for k in params_fstate:
-                    if k.startswith("vision_model.encoder.layers.") and k.endswith(".self_attn.q_proj.weight"):
-                        vis_layers = max(vis_layers, int(k.split(".")[3]) + 1)
-                config = {
-                    "text_config": {"hidden_size": text_hidden, "num_attention_heads": text_hidden // 64, "num_hidden_layers": text_layers,
-                                    "max_position_embeddings": text_ctx, "vocab_size": text_vocab},
-                    "vision_config": {"hidden_size": vis_hidden, "num_attention_heads": vis_hidden // 64, "num_hidden_layers": vis_layers,
-                                      "image_size": vis_img, "patch_size": vis_patch},
-                }
-            else:
+            if use_pytorch:
                 raise ValueError(f"Configuration could not be loaded for PyTorch model {model_name_or_path}")
+            # no config.json: the architecture from the tensor shapes (models/clip.py:213-252); head width 64 on both towers
+
+            def depth(tower):
+                return max((int(k.split(".")[3]) + 1 for k in hf if k.startswith(f"{tower}.encoder.layers.") and k.endswith(".self_attn.q_proj.weight")),
+                           default=0)
+
+            tok = hf["text_model.embeddings.token_embedding.weight"]
+            vw = hf["vision_model.embeddings.class_embedding"].shape[0]
+            vp = hf["vision_model.embeddings.patch_embedding.weight"].shape[2]
+            grid = int((hf["vision_model.embeddings.position_embedding.weight"].shape[0] - 1) ** 0.5)
+            config = {
+                "text_config": {"hidden_size": tok.shape[1], "num_attention_heads": tok.shape[1] // 64, "num_hidden_layers": depth("text_model"),
+                                "max_position_embeddings": hf["text_model.embeddings.position_embedding.weight"].shape[0], "vocab_size": tok.shape[0]},
+                "vision_config": {"hidden_size": vw, "num_attention_heads": vw // 64, "num_hidden_layers": depth("vision_model"),
+                                  "image_size": grid * vp, "patch_size": vp},
+            }
         tc, vc = config["text_config"], config["vision_config"]
-        with nn.deferred_init():  # every parameter is overwritten below (and asserted to be)
+        with nn.deferred_init():  # every parameter is replaced below (and asserted to be)
             model = cls(image_resolution=vc["image_size"], vision_layers=vc["num_hidden_layers"], vision_width=vc["hidden_size"],
                         vision_patch_size=vc["patch_size"], context_length=tc["max_position_embeddings"], vocab_size=tc["vocab_size"],
                         transformer_width=tc["hidden_size"], transformer_heads=tc["num_attention_heads"],
                         transformer_layers=tc["num_hidden_layers"], mesh=mesh, dtype=dtype, param_dtype=dtype)
-        flax_params = model.flat_params()
-        mapping = {
-            "logit_scale": "logit_scale",
-            "positional_embedding": "text_model.embeddings.position_embedding.weight",
-            "token_embedding.embedding": "text_model.embeddings.token_embedding.weight",
-            "ln_final.scale": "text_model.final_layer_norm.weight",
-            "ln_final.bias": "text_model.final_layer_norm.bias",
-            "text_projection.kernel": "text_projection.weight",
-            "vision_model.cls_token": "vision_model.embeddings.class_embedding",
-            "vision_model.position_embeddings": "vision_model.embeddings.position_embedding.weight",
-            "vision_model.patch_embeddings.kernel": "vision_model.embeddings.patch_embedding.weight",
-            "vision_model.ln_pre.scale": "vision_model.pre_layrnorm.weight",
-            "vision_model.ln_pre.bias": "vision_model.pre_layrnorm.bias",
-            "vision_model.ln_post.scale": "vision_model.post_layernorm.weight",
-            "vision_model.ln_post.bias": "vision_model.post_layernorm.bias",
-            "visual_projection.kernel": "visual_projection.weight",
-        }
+        v = "vision_model."
+        rules = [
+            ("logit_scale", "logit_scale", L.ASIS),
+            ("positional_embedding", "text_model.embeddings.position_embedding.weight", L.ASIS),
+            ("token_embedding.embedding", "text_model.embeddings.token_embedding.weight", L.ASIS),
+            ("ln_final.scale", "text_model.final_layer_norm.weight", L.ASIS),
+            ("ln_final.bias", "text_model.final_layer_norm.bias", L.ASIS),
+            ("text_projection.kernel", "text_projection.weight", L.LINEAR),
+            (v + "cls_token", v + "embeddings.class_embedding", L.ASIS),               # (D) -> (1,1,D)      models/clip.py:358-359
+            (v + "position_embeddings", v + "embeddings.position_embedding.weight", L.ASIS),  # (S,D) -> (1,S,D)    :360-361
+            (v + "patch_embeddings.kernel", v + "embeddings.patch_embedding.weight", L.CONV),
+            (v + "ln_pre.scale", v + "pre_layrnorm.weight", L.ASIS),                   # [sic] HF's spelling
+            (v + "ln_pre.bias", v + "pre_layrnorm.bias", L.ASIS),
+            (v + "ln_post.scale", v + "post_layernorm.weight", L.ASIS),
+            (v + "ln_post.bias", v + "post_layernorm.bias", L.ASIS),
+            ("visual_projection.kernel", "visual_projection.weight", L.LINEAR),
+        ]
         for i in range(tc["num_hidden_layers"]):
-            hf_block_mapping(mapping, f"text_model.blocks.layers.{i}.", f"text_model.encoder.layers.{i}.")
+            rules += L.block_rules(f"text_model.blocks.layers.{i}.", f"text_model.encoder.layers.{i}.", L.CLIP_BLOCK)
         for i in range(vc["num_hidden_layers"]):
-            hf_block_mapping(mapping, f"vision_model.transformer.blocks.layers.{i}.", f"vision_model.encoder.layers.{i}.")
-
-        nonvisited = set(flax_params.keys())
-        used_hf_keys: Set[str] = set()
-        for dst, src in mapping.items():
-            if dst not in flax_params or src not in params_fstate:
-                continue
-            used_hf_keys.add(src)
-            nonvisited.discard(dst)
-            v = params_fstate[src].to(torch.float32)
-            is_text = dst.startswith("text_model")
-            hidden = tc["hidden_size"] if is_text else vc["hidden_size"]
-            heads = tc["num_attention_heads"] if is_text else vc["hidden_size"] // 64
-            if dst == "vision_model.patch_embeddings.kernel":
-                v = v.permute(2, 3, 1, 0)
-            elif dst == "vision_model.cls_token":
-                v = v.reshape(1, 1, -1)
-            elif dst == "vision_model.position_embeddings":
-                v = v.reshape(1, v.shape[0], v.shape[1])
-            elif ".self_attn." in src:
-                v = transform_attn(v, src, hidden, heads)
-            elif dst in ("token_embedding.embedding", "positional_embedding"):
-                pass
-            elif src.endswith("weight") and v.ndim == 2:
-                v = v.T
-            if tuple(v.shape) != tuple(flax_params[dst].shape):
-                raise ValueError(f"Shape mismatch for {dst} (Flax) vs {src} (HF): {tuple(flax_params[dst].shape)} (expected) != {tuple(v.shape)} (actual)")
-            model.set_flat_param(dst, v)
-        assert len(nonvisited) == 0, f"Some Flax CLIP model parameters were not visited: {sorted(list(nonvisited))}"
-        leftover = set(params_fstate.keys()) - used_hf_keys
-        known_unused = {"text_model.embeddings.position_ids", "vision_model.embeddings.position_ids"}
-        unexpected = leftover - known_unused
-        assert len(unexpected) == 0, f"Some unexpected HuggingFace checkpoint parameters were not used: {sorted(list(unexpected))}"
+            rules += L.block_rules(f"{v}transformer.blocks.layers.{i}.", f"{v}encoder.layers.{i}.", L.CLIP_BLOCK)
+        # models/clip.py:343-345 skips table entries that are absent on either side, then insists that nothing is left over (:405-414)
+        L.apply_mapping(model, hf, rules, missing="skip", shape_error=ValueError, what="CLIP ")
         return model

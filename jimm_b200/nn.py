@@ -93,8 +93,28 @@ def compute_dtype_code(dtype) -> int:
     raise ValueError(f"Unsupported dtype {dtype!r}: expected float32, float16 or bfloat16")
 
 
+class LazyParam:
+    """A parameter whose value is a VIEW of checkpoint memory (e.g. the mmap of a safetensors file) in its stored dtype:
+        transposed=False:  flax value = base.reshape(shape)
+        transposed=True :  base is the 2-D [N, K] transpose of the flax kernel's (K, N) view -- a HuggingFace (out, in) weight as stored;
+                           flax value = base.T.reshape(shape)  (models/vit.py:241-250)
+    Nothing is converted or copied on the CPU: the CUDA library receives the pointer (jimm_model_set_param_ref) and casts / packs on
+    the GPU.  `materialize()` produces the fp32 tensor in the reference's layout for code that wants to look at the value."""
+
+    __slots__ = ("base", "shape", "transposed")
+
+    def __init__(self, base: torch.Tensor, shape, transposed: bool = False):
+        self.base, self.shape, self.transposed = base, tuple(int(d) for d in shape), bool(transposed)
+
+    def materialize(self) -> torch.Tensor:
+        t = self.base.to(torch.float32)
+        if self.transposed:
+            t = t.reshape(t.shape[0], -1).T
+        return t.reshape(self.shape).contiguous()
+
+
 class Module:
-    """Parameter-tree node.  Leaves are torch fp32 CPU tensors; children are Modules."""
+    """Parameter-tree node.  Leaves are torch fp32 CPU tensors (or `LazyParam` views of a checkpoint); children are Modules."""
 
     def __init__(self):
         object.__setattr__(self, "_params", {})
@@ -115,26 +135,36 @@ class Module:
             return ch[name]
         pr = object.__getattribute__(self, "_params")
         if name in pr:
-            return pr[name]
+            v = pr[name]
+            return v.materialize() if isinstance(v, LazyParam) else v
         raise AttributeError(f"{type(self).__name__!s} has no attribute {name!r}")
 
     # -- flat state (== the reference's flat-state keys joined with '.') --
-    def flat_params(self, prefix: str = "") -> Dict[str, torch.Tensor]:
+    def flat_params(self, prefix: str = "", raw: bool = False) -> Dict[str, torch.Tensor]:
+        """{flax path: fp32 tensor in the reference's layout}; raw=True keeps `LazyParam` entries as they are (the native hand-off)."""
         out: Dict[str, torch.Tensor] = {}
         for k, v in self._params.items():
-            out[prefix + k] = v
+            out[prefix + k] = v if raw or not isinstance(v, LazyParam) else v.materialize()
         for k, c in self._children.items():
-            out.update(c.flat_params(prefix + k + "."))
+            out.update(c.flat_params(prefix + k + ".", raw))
         return out
 
-    def set_flat_param(self, path: str, value: torch.Tensor):
+    def flat_param_shapes(self, prefix: str = "") -> Dict[str, Tuple[int, ...]]:
+        out: Dict[str, Tuple[int, ...]] = {}
+        for k, v in self._params.items():
+            out[prefix + k] = tuple(v.shape)
+        for k, c in self._children.items():
+            out.update(c.flat_param_shapes(prefix + k + "."))
+        return out
+
+    def set_flat_param(self, path: str, value):
         parts = path.split(".")
         node = self
         for p in parts[:-1]:
             node = node._children[p]
         if parts[-1] not in node._params:
             raise KeyError(path)
-        node._params[parts[-1]] = value.detach().to(torch.float32).contiguous()
+        node._params[parts[-1]] = value if isinstance(value, LazyParam) else value.detach().to(torch.float32).contiguous()
         self._invalidate()
 
     def _invalidate(self):

@@ -24,9 +24,24 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     for _ in range(3):
         bw.step_host()
     ms32, _ = bw.timed(bw.step_host, 20)
-    print(f"slices={os.environ.get('JIMM_HOST_SLICES','auto'):8s} device {ms/20:.3f} ms  e2e u8 {ms8/20:.3f} ms  e2e f32 {ms32/20:.3f} ms", flush=True)
+    ms_again, _ = bw.timed(bw.step_dev, 20)
+    state = {"pending": None}
+
+    def step_async():
+        nxt = bw.model.forward_async(bw.u8_host)
+        res = state["pending"].result() if state["pending"] is not None else None
+        state["pending"] = nxt
+        return res
+
+    for _ in range(3):
+        step_async()
+    msp, _ = bw.timed(step_async, 20)
+    state["pending"].result()
+    ms_last, _ = bw.timed(bw.step_dev, 20)
+    print(f"slices={os.environ.get('JIMM_HOST_SLICES','auto'):8s} device {ms/20:.3f} ms  e2e u8 {ms8/20:.3f} ms  e2e f32 {ms32/20:.3f} ms  device again {ms_again/20:.3f}  "
+          f"u8 async depth 2 {msp/20:.3f}  device last {ms_last/20:.3f}", flush=True)
 else:
-    for sl in (None, "256", "128", "86,85", "32"):
+    for sl in (None,):
         env = dict(os.environ)
         if sl:
             env["JIMM_HOST_SLICES"] = sl
