@@ -331,10 +331,16 @@ class Bench:
         self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        dbg = [] if os.environ.get("JIMM_BENCH_DEBUG") else None
         for _ in range(steps):
+            t0 = time.perf_counter()
             out = fn()
+            if dbg is not None:
+                dbg.append((time.perf_counter() - t0) * 1e3)
         e1.record()
         self.barrier()
+        if dbg is not None:
+            print(f"[bench debug] rank {self.rank} {getattr(fn, '__name__', 'fn')}: " + " ".join(f"{t:.2f}" for t in dbg), file=sys.stderr, flush=True)
         return self.jd.max_over_ranks(e0.elapsed_time(e1)), out
 
     def rate(self, ms_total, steps):

@@ -73,6 +73,10 @@ struct EpiDev {
   int debug;
   int reverse;
   int tok_pad, tok_off;  // > 0: 3-D token-scatter reduce-add (see GemmEpilogue)
+  // Tail splitting (pair mode): the static round-robin schedule costs a whole round for the last `tail` tiles even when they occupy a
+  // few of the CTA pairs.  When tail * parts <= #pairs those tiles are cut into `parts` (2 or 4) column slices of 256 / parts columns,
+  // so the last round takes ~1 / parts of a round: virtual tiles [0, full) are whole tiles, [full, full + tail * parts) the slices.
+  int full_tiles, tail_parts;
   int vec;  // 1: N / ldo / ldr multiples of 4 and 16-byte aligned pointers -> vector accesses allowed (generic path)
 };
 
@@ -144,7 +148,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volat
 // before the math / staging / store of the last box (the data is in registers by then), not after the whole epilogue.
 template <int OUT, int ACT, int NBUF, typename Release>
 __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const EpiDev& epi, uint32_t taddr, const float* sbias, uint8_t* tbuf0,
-                                             int lane, int row_base, int n_tile0, int c_begin, uint32_t& box_count, Release&& release) {
+                                             int lane, int row_base, int n_tile0, int c_begin, int c_len, uint32_t& box_count, Release&& release) {
   constexpr bool OUT16 = (OUT == OUT_H16 || OUT == OUT_BF16);
   constexpr int COLS_PER_BOX = OUT16 ? 64 : 32;
   const int N = epi.N;
@@ -152,11 +156,11 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
   bool released = false;
   if (n_tile0 + c_begin < N) tmem_ld_32x32b_x32(taddr + c_begin, r);
 #pragma unroll 1
-  for (int c = c_begin; c < c_begin + BN / 2; c += COLS_PER_BOX) {
+  for (int c = c_begin; c < c_begin + c_len; c += COLS_PER_BOX) {
     const int n0 = n_tile0 + c;
     if (n0 >= N) break;
     const int cn = c + COLS_PER_BOX;
-    const bool more = (cn < c_begin + BN / 2) && (n_tile0 + cn < N);
+    const bool more = (cn < c_begin + c_len) && (n_tile0 + cn < N);
     tmem_ld_wait();
     if constexpr (OUT16) tmem_ld_32x32b_x32(taddr + c + 32, r2);  // second half of this box, in flight during the math below
     else if (!more) { release(); released = true; }
@@ -303,6 +307,26 @@ __device__ __noinline__ void epilogue_generic(const EpiDev& epi, uint32_t taddr,
   }
 }
 
+struct TileCoord {
+  int m_blk, n_blk, n_off, width;  // columns [n_blk * BN + n_off, ... + width) of row block m_blk
+};
+// virtual tile index (already direction-adjusted) -> coordinates; identical in the three roles
+__device__ __forceinline__ TileCoord decode_tile(const EpiDev& e, int tv, int n_tiles) {
+  TileCoord t;
+  int te = tv;
+  t.n_off = 0;
+  t.width = BN;
+  if (tv >= e.full_tiles) {
+    const int j = tv - e.full_tiles;
+    te = e.full_tiles + j / e.tail_parts;
+    t.width = BN / e.tail_parts;
+    t.n_off = (j % e.tail_parts) * t.width;
+  }
+  t.m_blk = te / n_tiles;
+  t.n_blk = te - t.m_blk * n_tiles;
+  return t;
+}
+
 template <typename T, int OUT, int ACT, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -333,7 +357,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int M = epi.M, N = epi.N;
   const int m_tiles = (M + TILE_M - 1) / TILE_M, n_tiles = (N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int real_tiles = m_tiles * n_tiles;
+  const int num_tiles = epi.full_tiles + (real_tiles - epi.full_tiles) * epi.tail_parts;  // virtual tiles (== real_tiles without a split tail)
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
   const int tile0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -374,8 +399,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        const int te = epi.reverse ? num_tiles - 1 - tile : tile;
-        const int m_blk = te / n_tiles, n_blk = te - m_blk * n_tiles;
+        const TileCoord tc = decode_tile(epi, epi.reverse ? num_tiles - 1 - tile : tile, n_tiles);
+        const int m_blk = tc.m_blk;
+        // B rows of this CTA: its half of the tile's `width` columns (the box always carries BN / 2 rows; a slice uses the first width / 2)
+        const int b_row = tc.n_blk * BN + tc.n_off + (PAIR ? static_cast<int>(cta_rank) * (tc.width / 2) : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if constexpr (PAIR) {
@@ -387,14 +414,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             if (!dbg_no_load) {
               tma_load_2d_pair(smem_a + stage * A_STAGE_BYTES, &map_a, full_leader, kb * BK, m_blk * TILE_M + static_cast<int>(cta_rank) * BM);
-              tma_load_2d_pair(smem_b + stage * B_BYTES, &map_b, full_leader, kb * BK, n_blk * BN + static_cast<int>(cta_rank) * (BN / 2));
+              tma_load_2d_pair(smem_b + stage * B_BYTES, &map_b, full_leader, kb * BK, b_row);
             }
           } else if (dbg_no_load) {
             mbar_arrive(&full_bar[stage]);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, &map_a, &full_bar[stage], kb * BK, m_blk * BM);
-            tma_load_2d(smem_b + stage * B_BYTES, &map_b, &full_bar[stage], kb * BK, n_blk * BN);
+            tma_load_2d(smem_b + stage * B_BYTES, &map_b, &full_bar[stage], kb * BK, b_row);
           }
           if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
         }
@@ -410,6 +437,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+        const int tv = epi.reverse ? num_tiles - 1 - tile : tile;
+        const uint32_t idesc = tv >= epi.full_tiles ? make_idesc(Traits<T>::FMT, PAIR ? 2 * BM : BM, static_cast<uint32_t>(BN / epi.tail_parts)) : IDESC;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -421,8 +450,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const uint64_t bdesc = make_umma_desc_sw128(smem_u32(smem_b + stage * B_BYTES));
 #pragma unroll
             for (int k = 0; k < BK / UK; ++k) {  // descriptors advance by 32 bytes (>> 4) per UMMA K step
-              if constexpr (PAIR) umma_ss_pair<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
-              else umma_ss<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), IDESC, (kb | k) != 0 ? 1u : 0u);
+              if constexpr (PAIR) umma_ss_pair<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_ss<Traits<T>::KIND>(tmem_d, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
             }
             if constexpr (PAIR) {
               tcgen05_commit_pair(&empty_bar[stage]);  // frees this stage in BOTH CTAs once the MMAs above retire
@@ -445,17 +474,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint32_t acc_phase = 0, box_count = 0;
     const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      const int te = epi.reverse ? num_tiles - 1 - tile : tile;
-      const int m_blk = te / n_tiles, n_blk = te - m_blk * n_tiles;
+      const TileCoord tc = decode_tile(epi, epi.reverse ? num_tiles - 1 - tile : tile, n_tiles);
+      const int m_blk = tc.m_blk;
+      const int n_tile0 = tc.n_blk * BN + tc.n_off;  // first column of this (possibly sliced) tile
+      const int c_len = tc.width / 2;                // accumulator columns per column half
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BM + q * 32;
       if constexpr (OUT != OUT_GENERIC) {
         // per-tile bias copy (one coalesced 128-bit load per lane of two warps), overlapped with the wait for the MMAs
         named_bar_sync(1, EPI_WARPS * 32);  // every epilogue warp is done with the previous tile's bias
-        if (q == 0) {
-          const int col = n_blk * BN + half * (BN / 2) + lane * 4;
+        if (q == 0) {  // sbias[c] = bias[n_tile0 + c] for the accumulator columns c of this half
+          const int c = half * c_len + lane * 4;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (epi.bias && col < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + col));
-          *reinterpret_cast<float4*>(sbias + half * (BN / 2) + lane * 4) = b4;
+          if (epi.bias && lane * 4 < c_len && n_tile0 + c < N) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + n_tile0 + c));
+          if (lane * 4 < c_len) *reinterpret_cast<float4*>(sbias + c) = b4;
         }
         named_bar_sync(1, EPI_WARPS * 32);
       }
@@ -475,13 +506,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         release();
       } else if constexpr (OUT != OUT_GENERIC) {
         if (row_base < M)
-          epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES, lane, row_base, n_blk * BN,
-                                           half * (BN / 2), box_count, release);
+          epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES, lane, row_base, n_tile0,
+                                           half * c_len, c_len, box_count, release);
         else
           release();
       } else {
         if (half == 0 && row_base < M)
-          epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_blk * BN);
+          epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_tile0);
         release();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -665,6 +696,8 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.M = M; d.N = N;
   d.tok_pad = e.tok_pad; d.tok_off = e.tok_off;
   d.reverse = e.reverse;
+  d.full_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);  // overwritten by the pair-mode launch (its row blocks are 2 * BM)
+  d.tail_parts = 1;
   d.vec = epi_vec_ok(e, N);
   static int dbg = -1;
   if (dbg < 0) { const char* env = getenv("JIMM_GEMM_DEBUG"); dbg = env ? atoi(env) : 0; }
@@ -672,6 +705,11 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   return d;
 }
 
+static int tail_split_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* env = getenv("JIMM_GEMM_TAIL_SPLIT"); v = env ? atoi(env) : 1; }
+  return v;
+}
 static int pair_mode_enabled() {
   static int v = -1;
   if (v < 0) { const char* env = getenv("JIMM_GEMM_PAIR"); v = env ? atoi(env) : 1; }
@@ -686,12 +724,22 @@ static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
     JIMM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tcgen05_kernel<T, OUT, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   }
   const int n_tiles = (p->N + BN - 1) / BN;
-  const EpiDev d = to_dev(p->epi, M, p->N);
+  EpiDev d = to_dev(p->epi, M, p->N);
   if (OUT != OUT_GENERIC && pair_mode_enabled() && M >= 512) {
     // CTA pairs: 256 x 256 tiles, cluster (2,1,1), one pair per two SMs
     const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * n_tiles;
     const int max_pairs = device_sm_count() / 2;
-    const int pairs = tiles < max_pairs ? tiles : max_pairs;
+    // split the tail round into column slices when that shortens it (see EpiDev): 16-bit outputs store 64-column boxes, so a column
+    // half must keep >= 64 columns (parts <= 2); 32-bit outputs store 32-column boxes (parts <= 4)
+    int tail = tiles % max_pairs, parts = 1;
+    constexpr int kMaxParts = (OUT == OUT_H16 || OUT == OUT_BF16) ? 2 : 4;
+    if (tail_split_enabled() && tail > 0) {
+      while (parts * 2 <= kMaxParts && tail * parts * 2 <= max_pairs) parts *= 2;
+    }
+    d.full_tiles = parts > 1 ? tiles - tail : tiles;
+    d.tail_parts = parts;
+    const int vtiles = d.full_tiles + (tiles - d.full_tiles) * parts;
+    const int pairs = vtiles < max_pairs ? vtiles : max_pairs;
     JIMM_CUDA_CHECK(launch_k(gemm_tcgen05_kernel<T, OUT, ACT, true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, 2, true,
                              p->map_a, p->map_b_pair, p->map_c, d, p->K));
     note_launch();
