@@ -59,10 +59,23 @@ class _NativeOwner:
         object.__setattr__(self, "_compute_dtype", nn.compute_dtype_code(dtype))
         object.__setattr__(self, "_max_batch", default_max_batch())
 
+    @staticmethod
+    def _release_native(n):
+        """Free a native handle.  If it owns an NVLink gather buffer, the peers have it mapped through CUDA IPC and may still be storing
+        into it: every rank rebuilds at the same point of the program (same batch on every rank), so all of them drain their streams
+        and meet at a barrier before anybody frees."""
+        if getattr(n, "_comm", None) is not None:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                torch.cuda.synchronize(n.device)
+                dist.barrier()
+        n.close()
+
     def _invalidate(self):
         n = getattr(self, "_native", None)
         if n is not None:
-            n.close()
+            self._release_native(n)
         object.__setattr__(self, "_native", None)
 
     def _native_config(self) -> _lib.Config:
@@ -75,7 +88,7 @@ class _NativeOwner:
         if n is not None and (not require or batch <= n.max_batch):
             return n
         if n is not None:
-            n.close()
+            self._release_native(n)
         mb = max(self._max_batch, int(batch) if require else 1)
         n = NativeModel(self._native_config(), self.flat_params(raw=True), mb)
         n.preproc = self._preproc

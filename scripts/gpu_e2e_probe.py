@@ -1,48 +1,43 @@
-"""e2e (host uint8 frames -> logits on host) of ViT-B/16 B=256 under different host-slice layouts (JIMM_HOST_SLICES) vs the device-resident step."""
+"""e2e diagnostics for ViT-B/16 B=256: device-resident step interleaved with the host paths (uint8 sync / fp32 sync / uint8 async depth 2),
+20 steps each, in one process -- separates clock drift under the power cap from path effects."""
 import os
-import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-if len(sys.argv) > 1 and sys.argv[1] == "child":
-    import torch
+import torch
 
-    import bench
-    from jimm_b200 import _lib, build
+import bench
+from jimm_b200 import _lib, build
 
-    build.build()
-    lib = _lib.load()
-    torch.cuda.set_device(0)
-    bw = bench.Bench("vit_b16", 0, 0, 1, 0, lib)
-    for _ in range(5):
-        bw.step_dev()
-    ms, _ = bw.timed(bw.step_dev, 20)
+build.build()
+lib = _lib.load()
+torch.cuda.set_device(0)
+bw = bench.Bench("vit_b16", 0, 0, 1, 0, lib)
+state = {"pending": None}
+
+
+def step_async():
+    nxt = bw.model.forward_async(bw.u8_host)
+    res = state["pending"].result() if state["pending"] is not None else None
+    state["pending"] = nxt
+    return res
+
+
+def run(name, fn, n=20):
     for _ in range(3):
-        bw.step_host_u8()
-    ms8, _ = bw.timed(bw.step_host_u8, 20)
-    for _ in range(3):
-        bw.step_host()
-    ms32, _ = bw.timed(bw.step_host, 20)
-    ms_again, _ = bw.timed(bw.step_dev, 20)
-    state = {"pending": None}
+        fn()
+    if state["pending"] is not None and fn is not step_async:
+        state["pending"].result()
+        state["pending"] = None
+    ms, _ = bw.timed(fn, n)
+    if fn is step_async:
+        state["pending"].result()
+        state["pending"] = None
+    print(f"{name:10s} {ms/n:.3f} ms", flush=True)
 
-    def step_async():
-        nxt = bw.model.forward_async(bw.u8_host)
-        res = state["pending"].result() if state["pending"] is not None else None
-        state["pending"] = nxt
-        return res
 
-    for _ in range(3):
-        step_async()
-    msp, _ = bw.timed(step_async, 20)
-    state["pending"].result()
-    ms_last, _ = bw.timed(bw.step_dev, 20)
-    print(f"slices={os.environ.get('JIMM_HOST_SLICES','auto'):8s} device {ms/20:.3f} ms  e2e u8 {ms8/20:.3f} ms  e2e f32 {ms32/20:.3f} ms  device again {ms_again/20:.3f}  "
-          f"u8 async depth 2 {msp/20:.3f}  device last {ms_last/20:.3f}", flush=True)
-else:
-    for sl in (None,):
-        env = dict(os.environ)
-        if sl:
-            env["JIMM_HOST_SLICES"] = sl
-        subprocess.run([sys.executable, __file__, "child"], env=env)
+order = os.environ.get("ORDER", "dev,u8,dev,u8,f32,dev,u8,u8,async,dev,f32,u8,dev").split(",")
+fns = {"dev": bw.step_dev, "u8": bw.step_host_u8, "f32": bw.step_host, "async": step_async}
+for o in order:
+    run(o, fns[o])

@@ -226,3 +226,41 @@ def test_bench_clock_sampler_window():
     assert [r for _, r in s.selected_rows()] == ["w2", "w3", "w4"]
     s.rows.append((10.5, "post"))  # the caller kept the load running until a sample landed
     assert [r for _, r in s.selected_rows()] == ["post"]
+
+
+def test_zero_copy_checkpoint_views(golden_dir, tmp_path):
+    """the loader hands the CUDA library VIEWS of the checkpoint -- safetensors are memory-mapped (no tensor is copied or
+    converted on the CPU), kernels stay in their HuggingFace (out, in) order behind a transposed `LazyParam`, and the materialised
+    values are exactly the reference's transforms; fp16 / bf16 checkpoints (safetensors and pytorch_model.bin) keep their dtype."""
+    from safetensors.torch import load_file, save_file
+
+    from jimm_b200.common.utils import load_params_and_config, read_safetensors_mmap
+    from jimm_b200.models import VisionTransformer
+    from jimm_b200.nn import LazyParam
+
+    src = os.path.join(golden_dir, "tiny_vit", "model.safetensors")
+    ref = load_file(src)
+    views = read_safetensors_mmap(src)
+    assert set(views) == set(ref) and all(torch.equal(views[k], ref[k]) for k in ref)
+    m = VisionTransformer.from_pretrained(src)
+    raw = m.flat_params(raw=True)
+    k = "encoder.transformer.blocks.layers.0.attn.query.kernel"
+    assert isinstance(raw[k], LazyParam) and raw[k].transposed
+    hf = views["vit.encoder.layer.0.attention.attention.query.weight"]
+    ptr = raw[k].base.data_ptr()
+    spans = [tuple(int(x, 16) for x in line.split()[0].split("-")) for line in open("/proc/self/maps") if line.rstrip().endswith("tiny_vit/model.safetensors")]
+    assert any(lo <= ptr < hi for lo, hi in spans), "the kernel must be handed over as a view of the mapped file, not a copy"
+    assert torch.equal(m.flat_params()[k], hf.T.reshape(raw[k].shape))  # models/vit.py:241-243
+    # 16-bit checkpoints: same tree, values rounded once by the checkpoint's own dtype
+    for dt, sub in ((torch.bfloat16, "bf16"), (torch.float16, "f16")):
+        d = tmp_path / sub
+        d.mkdir()
+        save_file({kk: v.to(dt) for kk, v in ref.items()}, str(d / "model.safetensors"))
+        shutil.copy(os.path.join(golden_dir, "tiny_vit", "config.json"), d / "config.json")
+        torch.save({kk: v.to(dt) for kk, v in ref.items()}, str(d / "pytorch_model.bin"))
+        for path, use_pt in ((str(d / "model.safetensors"), False), (str(d), True)):
+            params, cfg = load_params_and_config(path, use_pt)
+            assert cfg["hidden_size"] == 128 and all(v.dtype == dt for v in params.values())
+            m16 = VisionTransformer.from_pretrained(path, use_pytorch=use_pt, dtype=dt)
+            assert m16.flat_params(raw=True)[k].base.dtype == dt
+            assert torch.equal(m16.flat_params()[k], hf.to(dt).float().T.reshape(raw[k].shape))
