@@ -203,15 +203,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
         const float th_raw = 8.0f / p.scale_log2;
         uint32_t r[32], rn[32];
+        // One chunk = 32 scores of the row.  The dependent chains are kept short (four interleaved max / sum chains instead of one of
+        // 16) and, after the first chunk, the exponentials are issued SPECULATIVELY against the current reference maximum while the
+        // chunk maximum is still being reduced: with one warp per SMSP per stream the MUFU was only ~48 % busy because every chunk
+        // serialised max chain -> raise vote -> 32 ex2 -> sum chain (profiles/r2_b_attention.md).  A raise (rare) discards the
+        // speculative values and redoes the chunk exactly.
         auto softmax_chunk = [&](const uint32_t (&sv)[32], int c) {
-          // chunk maximum over this row's valid keys
-          float cm = -INFINITY;
-          if (c < n_full) {
+          const bool full = c < n_full;
+          uint32_t pk[16];
+          float cm;
+          if (full) {
+            float q0 = -INFINITY, q1 = -INFINITY, q2 = -INFINITY, q3 = -INFINITY;
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) cm = fmax3(cm, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+            for (int j = 0; j < 32; j += 8) {
+              q0 = fmax3(q0, __uint_as_float(sv[j]), __uint_as_float(sv[j + 1]));
+              q1 = fmax3(q1, __uint_as_float(sv[j + 2]), __uint_as_float(sv[j + 3]));
+              q2 = fmax3(q2, __uint_as_float(sv[j + 4]), __uint_as_float(sv[j + 5]));
+              q3 = fmax3(q3, __uint_as_float(sv[j + 6]), __uint_as_float(sv[j + 7]));
+            }
+            cm = fmaxf(fmaxf(q0, q1), fmaxf(q2, q3));
           } else {
+            cm = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 32; ++j) cm = (c * 32 + j < kmax) ? fmaxf(cm, __uint_as_float(sv[j])) : cm;
+          }
+          // exponentials of a full chunk against reference maximum `mref`: packed P values + four partial row sums
+          auto exp_full = [&](float mref, float2& sum) {
+            const float2 mo2 = make_float2(-mref * p.scale_log2, -mref * p.scale_log2);
+            float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const float2 a0 = ffma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, mo2);
+              const float2 a1 = ffma2(make_float2(__uint_as_float(sv[j + 2]), __uint_as_float(sv[j + 3])), sc2, mo2);
+              const float2 a2 = ffma2(make_float2(__uint_as_float(sv[j + 4]), __uint_as_float(sv[j + 5])), sc2, mo2);
+              const float2 a3 = ffma2(make_float2(__uint_as_float(sv[j + 6]), __uint_as_float(sv[j + 7])), sc2, mo2);
+              const float2 e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y)), e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+              const float2 e2 = make_float2(ex2_approx(a2.x), ex2_approx(a2.y)), e3 = make_float2(ex2_approx(a3.x), ex2_approx(a3.y));
+              s0 = fadd2(s0, e0); s1 = fadd2(s1, e1); s2 = fadd2(s2, e2); s3 = fadd2(s3, e3);
+              pk[(j >> 1)] = pack2(e0.x, e0.y, FMT == 0 ? 1 : 2);
+              pk[(j >> 1) + 1] = pack2(e1.x, e1.y, FMT == 0 ? 1 : 2);
+              pk[(j >> 1) + 2] = pack2(e2.x, e2.y, FMT == 0 ? 1 : 2);
+              pk[(j >> 1) + 3] = pack2(e3.x, e3.y, FMT == 0 ? 1 : 2);
+            }
+            sum = fadd2(fadd2(s0, s1), fadd2(s2, s3));
+          };
+          if (full && c > 0) {  // speculative: m_ref is finite after the first chunk (key 0 is valid for every row)
+            float2 sum;
+            exp_full(m_ref, sum);
+            if (!__any_sync(0xffffffffu, cm > m_ref + th_raw)) {
+              l2 = fadd2(l2, sum);
+              tmem_st_32x32b_x16(taddr + c * 16, pk);
+              return;
+            }
           }
           const bool raise = cm > m_ref + th_raw;  // always true for the first valid chunk (m_ref = -inf)
           if (__any_sync(0xffffffffu, raise)) {
@@ -232,17 +275,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
               }
             }
           }
-          const float2 mo2 = make_float2(-m_ref * p.scale_log2, -m_ref * p.scale_log2);
-          uint32_t pk[16];
-          if (c < n_full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float2 a = ffma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, mo2);
-              const float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
-              l2 = fadd2(l2, e);
-              pk[j >> 1] = pack2(e.x, e.y, FMT == 0 ? 1 : 2);
-            }
+          if (full) {
+            float2 sum;
+            exp_full(m_ref, sum);
+            l2 = fadd2(l2, sum);
           } else {
+            const float2 mo2 = make_float2(-m_ref * p.scale_log2, -m_ref * p.scale_log2);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
               const float2 a = ffma2(make_float2(__uint_as_float(sv[j]), __uint_as_float(sv[j + 1])), sc2, mo2);
