@@ -194,6 +194,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         const int n_live = (kmax_warp + 31) / 32, n_full = kmin_warp / 32;
         mbar_wait(&s_full[g], sp);
         tcgen05_fence_after();
+        if (t * 128 + q * 32 >= S) {
+          // No query row of this warp exists (S = 197: rows 224..255 of the second tile; S = 50: the upper two warps): keep the barrier
+          // protocol, skip the work.  tcgen05.ld moves 64 B/clk/SM and the score tile is the bulk of it -- a dead warp's share (1/8 of
+          // an item at S = 197) is pure loss; its P / O rows are garbage that the 3-D output map clips.
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[g]);
+          mbar_wait(&o_full[g], sp);
+          tcgen05_fence_after();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&slot_free[g]);
+          continue;
+        }
         // ---- single pass over S (the kernel is bound by TMEM read bandwidth, ~64 B/clk/SM: reading the scores twice for an
         //      exact row max first cost 45 % more; profiles/r1_d).  Lazy-rescale softmax: p = exp2((s - m_ref) * scale) against a
         //      reference maximum that is only raised when a chunk's maximum exceeds it by more than 2^8 in the exp2 domain (so
@@ -297,15 +311,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         // chunks c+1 .. c+3 that may be in flight start at column 32(c+1) >= 16c+16.
         // two x32 loads per tcgen05.wait::ld (the wait is a MEMBAR-class instruction: halve their number); a buffer is refilled
         // as soon as its chunk has been consumed, so the loads of chunks c+2 / c+3 fly during the math of chunks c / c+1
-        tmem_ld_32x32b_x32(taddr, r);
-        if (n_live > 1) tmem_ld_32x32b_x32(taddr + 32, rn);
+        // the MMA wrote Nk = ceil16(S) columns: when the last chunk holds only 16 of them, load 16 (its other 16 registers keep stale
+        // values, all beyond kmax and masked) -- 7 % of the score bytes at S = 197
+        auto ld_chunk = [&](int c, uint32_t (&buf)[32]) {
+          if (c * 32 + 16 >= p.Nk) tmem_ld_32x32b_x16(taddr + c * 32, reinterpret_cast<uint32_t (&)[16]>(buf));
+          else tmem_ld_32x32b_x32(taddr + c * 32, buf);
+        };
+        ld_chunk(0, r);
+        if (n_live > 1) ld_chunk(1, rn);
         for (int c = 0; c < n_live; c += 2) {
           tmem_ld_wait();
           softmax_chunk(r, c);
-          if (c + 2 < n_live) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, r);
+          if (c + 2 < n_live) ld_chunk(c + 2, r);
           if (c + 1 < n_live) {
             softmax_chunk(rn, c + 1);
-            if (c + 3 < n_live) tmem_ld_32x32b_x32(taddr + (c + 3) * 32, rn);
+            if (c + 3 < n_live) ld_chunk(c + 3, rn);
           }
         }
         const float l = l2.x + l2.y;
