@@ -416,6 +416,17 @@ def collective_leg(args, rank, world, local, lib):
     for _ in range(5):
         lg = n.comm_logits(ie, te)
     ms_k, lg = bw.timed(lambda: n.comm_logits(ie, te), reps)
+    # per-call distribution (CUDA events around every call): the mean above includes whatever skew the two ranks' launch loops pick up
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    bw.barrier()
+    evs[0].record()
+    for i in range(reps):
+        lg = n.comm_logits(ie, te)
+        evs[i + 1].record()
+    bw.barrier()
+    per_call = sorted(evs[i].elapsed_time(evs[i + 1]) * 1e3 for i in range(reps))
+    us_median = bw.jd.max_over_ranks(per_call[reps // 2])
+    us_min, us_max = bw.jd.max_over_ranks(per_call[0]), bw.jd.max_over_ranks(per_call[-1])
     # NCCL baseline of the same exchange (normalise + all_gather_into_tensor + local logits), for context
     m.set_comm("nccl")
     for _ in range(5):
@@ -446,7 +457,7 @@ def collective_leg(args, rank, world, local, lib):
     dist.all_reduce(same, op=dist.ReduceOp.MIN)
     nccl_diff = bw.jd.max_over_ranks(float((lg_nccl - lg).abs().max()))
     bytes_per_peer = B * 2 * E * 4
-    us = ms_k / reps * 1e3
+    us = us_median
     egress = bytes_per_peer * (world - 1)
     return {
         "workload": WORKLOADS[wl][0] + f" x {world} GPUs = global batch {world * B}", "kernel": "comm_logits_kernel (csrc/comm.cu)",
@@ -455,7 +466,8 @@ def collective_leg(args, rank, world, local, lib):
         "value": bw.rate(ms, steps), "unit": "pairs/sec", "ms_per_step": ms / steps, "steps": steps,
         "e2e": {"value": bw.rate(ms_h, steps), "unit": "pairs/sec", "ms_per_step": ms_h / steps,
                 "h2d_bytes_per_step": bw.img_host.numel() * 4 + bw.ids_host.numel() * 4, "d2h_bytes_per_step": B * world * B * 4},
-        "us_per_call": us, "calls_timed": reps, "bytes_sent_per_peer": bytes_per_peer, "peers": world - 1,
+        "us_per_call": us, "us_per_call_stat": "median of per-call CUDA-event times, max over ranks", "us_per_call_mean": ms_k / reps * 1e3,
+        "us_per_call_min": us_min, "us_per_call_max": us_max, "calls_timed": reps, "bytes_sent_per_peer": bytes_per_peer, "peers": world - 1,
         "nvlink_egress_gbs": egress / (us * 1e-6) / 1e9, "nvlink_peak_gbs": 770.0, "nvlink_frac": egress / (us * 1e-6) / 1e9 / 770.0,
         "note": "latency-bound by construction: %.2f MiB per peer is %.1f us of NVLink time at 770 GB/s; the rest is normalise + flag barrier + "
                 "the [B_local, B_global] logits tile" % (bytes_per_peer / 2**20, bytes_per_peer / 770e9 * 1e6),

@@ -92,3 +92,110 @@ def test_sharded_contrastive_head(kind):
         # fp16 towers' error amplified by exp(logit_scale) (tests/test_parity_gpu.py LOGITS_TOL), recorded here
         record_parity(f"multi-GPU {kind} head, world {world}, rank {rank}", "logits row block", "float16", "fp32", 2e-3, max(errs))
         assert all(e < 2e-3 for e in errs), (rank, errs)
+
+
+def _worker_faults(rank, world, port, q):
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      JIMM_COMM_TIMEOUT_MS="300")
+    import torch.distributed as dist
+
+    from jimm_b200 import _lib
+    from jimm_b200 import dist as jd
+    from jimm_b200.models import CLIP
+
+    jd.init_from_env("nccl")
+    m = CLIP(64, 1, 64, 16, 8, 64, 64, 1, 1, dtype=torch.float16)
+    n = m.native(8, require=True)
+    n.comm_setup(8)
+    res = {}
+    ie, te = torch.randn(8, 64, device="cuda"), torch.randn(8, 64, device="cuda")
+    ok = n.comm_logits(ie, te)
+    torch.cuda.synchronize()
+    res["first_ok"] = bool(torch.isfinite(ok).all()) and n.lib.jimm_comm_status(n.handle) == 0
+    dist.barrier()
+    # 1) ranks disagree on B_local: every rank must see NaN logits and a sticky error naming the mismatch (never stale columns)
+    b = 8 if rank == 0 else 6
+    out = n.comm_logits(ie[:b], te[:b])
+    torch.cuda.synchronize()
+    res["mismatch_nan"] = bool(torch.isnan(out).all())
+    res["mismatch_rc"] = n.lib.jimm_comm_status(n.handle)
+    res["mismatch_msg"] = _lib.last_error()
+    try:
+        n.comm_logits(ie, te)
+        res["next_call_raises"] = False
+    except _lib.JimmError:
+        res["next_call_raises"] = True
+    dist.barrier()
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def _worker_timeout(rank, world, port, q):
+    import sys
+    import time
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                      JIMM_COMM_TIMEOUT_MS="300")
+    import torch.distributed as dist
+
+    from jimm_b200 import _lib
+    from jimm_b200 import dist as jd
+    from jimm_b200.models import CLIP
+
+    jd.init_from_env("nccl")
+    m = CLIP(64, 1, 64, 16, 8, 64, 64, 1, 1, dtype=torch.float16)
+    n = m.native(8, require=True)
+    n.comm_setup(8)
+    ie, te = torch.randn(8, 64, device="cuda"), torch.randn(8, 64, device="cuda")
+    res = {}
+    if rank == 0:  # rank 1 never joins this exchange: the kernel must give up after the timeout instead of spinning forever
+        t0 = time.time()
+        out = n.comm_logits(ie, te)
+        torch.cuda.synchronize()
+        res["seconds"] = time.time() - t0
+        res["nan"] = bool(torch.isnan(out).all())
+        res["rc"] = n.lib.jimm_comm_status(n.handle)
+        res["msg"] = _lib.last_error()
+    dist.barrier()
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def _run(worker, world=2):
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    return res
+
+
+@pytest.mark.timeout(400)
+def test_comm_rejects_mismatched_rows():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    res = _run(_worker_faults)
+    for rank, r in res.items():
+        assert r["first_ok"], (rank, r)
+        assert r["mismatch_nan"] and r["mismatch_rc"] != 0 and "different number of rows" in r["mismatch_msg"], (rank, r)
+        assert r["next_call_raises"], (rank, r)
+
+
+@pytest.mark.timeout(400)
+def test_comm_peer_timeout_is_bounded():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _run(_worker_timeout)[0]
+    assert r["nan"] and r["rc"] != 0 and "did not publish" in r["msg"], r
+    assert r["seconds"] < 30, r
