@@ -34,12 +34,29 @@ def _newest_dep() -> float:
     return max(t, os.path.getmtime(__file__))
 
 
+def _stale() -> bool:
+    return not os.path.exists(LIB) or os.path.getmtime(LIB) < _newest_dep()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    dep_t = _newest_dep()
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= dep_t:
+    if not force and not _stale():
         return LIB
+    # one builder at a time: under torchrun every rank calls build(); without the lock their nvcc runs overwrite each other's objects and
+    # a rank can dlopen a half-written library.  Whoever gets the lock second finds the library fresh and returns.
+    import fcntl
 
+    with open(os.path.join(OBJ, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> str:
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
@@ -55,10 +72,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    tmp = LIB + f".tmp{os.getpid()}"
+    cmd = [NVCC, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)  # atomic: a concurrent dlopen sees the old or the new library, never a partial one
     return LIB
 
 

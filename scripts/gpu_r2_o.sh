@@ -1,0 +1,19 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 300 -k "attention" > gpurun_out/kernels.log 2>&1; echo "attention tests rc=$?"; tail -n 4 gpurun_out/kernels.log
+timeout 200 python scripts/gpu_attn_perf.py > gpurun_out/attn_perf.log 2>&1; cat gpurun_out/attn_perf.log
+timeout 900 python -m pytest tests/test_parity_gpu.py -q -m gpu --timeout 600 -x -k "config3 or config5 or full_depth" > gpurun_out/parity.log 2>&1; echo "parity rc=$?"; tail -n 5 gpurun_out/parity.log
+for wl in vit_l16_map; do timeout 300 python bench.py --workload $wl --steps 5 --warmup 3 --no-cpu --no-extras 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('$wl', 'value', round(d['value'],1), 'ms', round(d['ms_per_step'],3), 'e2e', round(d['e2e']['value'],1), 'gemm frac', round(d['roofline']['frac'],3))
+"; done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29516 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_n2.log 2> gpurun_out/bench_n2.err; echo "bench_n2 rc=$?"; python - <<'PY'
+import json
+for l in open('gpurun_out/bench_n2.log'):
+    if l.startswith('{'):
+        d=json.loads(l); print('value',round(d['value']),'e2e',round(d['e2e']['value'])); c=d['collective']; print({k:v for k,v in c.items() if k not in ('workload','reference_step','note','kernel')})
+PY
+tail -3 gpurun_out/bench_n2.err
