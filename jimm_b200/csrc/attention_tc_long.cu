@@ -26,9 +26,6 @@
 namespace jimm {
 
 static constexpr int ATL_THREADS = 640;
-#ifndef ATL_POLY_EXP
-#define ATL_POLY_EXP 1  // share of the softmax exponentials evaluated by polynomial: 1 = every other pair, 0 = all on the MUFU
-#endif
 static constexpr int ATL_KB = 192;                          // keys per block
 static constexpr int ATL_Q_BYTES = 256 * 128;               // Q pair box
 static constexpr int ATL_KV_BYTES = ATL_KB * 128;           // K or V block box
@@ -284,9 +281,7 @@ attention_tc_long_kernel(const __grid_constant__ CUtensorMap map_q, const __grid
 #pragma unroll
             for (int jj = 0; jj < 32; jj += 2) {
               const float2 a = ffma2(make_float2(__uint_as_float(r[jj]), __uint_as_float(r[jj + 1])), sc2, mo2);
-              // every other pair of exponentials runs on the FMA / ALU pipes (ex2_poly2) instead of the MUFU: with 16 softmax warps the 4-lane
-              // MUFU of an SMSP was the queue the warps stood in (stall_mio on every MUFU.EX2, profiles/r2_b_attention.md)
-              float2 e = (ATL_POLY_EXP && (jj & 2)) ? ex2_poly2(a) : make_float2(ex2_approx(a.x), ex2_approx(a.y));
+              float2 e = make_float2(ex2_approx(a.x), ex2_approx(a.y));
               if (c >= n_full) {
                 e.x = (c * 32 + jj < kvalid) ? e.x : 0.f;
                 e.y = (c * 32 + jj + 1 < kvalid) ? e.y : 0.f;

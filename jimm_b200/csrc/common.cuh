@@ -359,26 +359,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// 2^x for a PAIR of fp32 values on the FMA / ALU pipes instead of the 4-lane MUFU (which the long-sequence softmax saturates: 16 exponentials per
-// clock per SM).  Cody-Waite: n = rint(x) through the 1.5 * 2^23 magic add, f = x - n in [-0.5, 0.5], 2^f by a degree-4 polynomial (relative
-// error < 5e-5, an order below the fp16 / bf16 rounding of P), then n is added to the exponent field.  x is clamped to >= -126.
-__device__ __forceinline__ float2 ex2_poly2(float2 x) {
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);
-  x.x = fmaxf(x.x, -126.0f);
-  x.y = fmaxf(x.y, -126.0f);
-  const float2 t = fadd2(x, magic);                                   // low mantissa bits of t hold rint(x)
-  const float2 n = fadd2(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = fadd2(x, make_float2(-n.x, -n.y));
-  float2 p = ffma2(f, make_float2(0.0096181291f, 0.0096181291f), make_float2(0.0555041087f, 0.0555041087f));
-  p = ffma2(p, f, make_float2(0.2402265070f, 0.2402265070f));
-  p = ffma2(p, f, make_float2(0.6931471806f, 0.6931471806f));
-  p = ffma2(p, f, make_float2(1.0f, 1.0f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));  // (t - magic) << 23: the magic's low bits are zero
-  r.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (thread i <- lane i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(

@@ -107,14 +107,15 @@ int layernorm_run(const float* x, int ldx, int group, int row_off, const int* ro
 // ------------------------------------------------------------------------------------------
 template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int H, int W, int C, int P, int gh, int gw, size_t total4, int rps) {
-  const size_t i4 = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i4 >= total4) return;
-  const size_t e = i4 * 4;
+patchify_kernel(const InT* __restrict__ img, OutT* __restrict__ out, int B, int H, int W, int C, int P, int gh, int gw, int per_img4, int rps) {
+  // blockIdx.y = image, 32-bit index arithmetic inside the image (the 64-bit divisions of a flat index made this kernel XU-bound:
+  // 61 us for 231 MB, profiles/r2_kernels.md)
+  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i4 >= per_img4) return;
+  const int b = blockIdx.y;
+  const int rem = i4 * 4;
   const int WC = W * C, PC = P * C;
-  const size_t img_elems = static_cast<size_t>(H) * WC;
-  const int b = static_cast<int>(e / img_elems);
-  const int rem = static_cast<int>(e - static_cast<size_t>(b) * img_elems);
+  const size_t e = static_cast<size_t>(b) * H * WC + rem;
   const int y = rem / WC, xc = rem - y * WC;
   const int gx = xc / PC, kc = xc - gx * PC;
   const int gy = y / P, ky = y - gy * P;
@@ -147,14 +148,19 @@ template <typename InT>
 static int patchify_dispatch(const void* img, int B, int H, int W, int C, int P, void* out, int out_type, cudaStream_t stream, int rps) {
   const int gh = H / P, gw = W / P;
   if (rps <= 0) rps = gh * gw;
-  const size_t total4 = static_cast<size_t>(B) * H * W * C / 4;
+  const int per_img4 = H * W * C / 4;
   const int threads = 256;
-  const unsigned grid = static_cast<unsigned>((total4 + threads - 1) / threads);
   const InT* in = static_cast<const InT*>(img);
-  if (out_type == DT_F32) patchify_kernel<InT, float><<<grid, threads, 0, stream>>>(in, static_cast<float*>(out), B, H, W, C, P, gh, gw, total4, rps);
-  else if (out_type == DT_TF32) patchify_kernel<InT, tf32_t><<<grid, threads, 0, stream>>>(in, static_cast<tf32_t*>(out), B, H, W, C, P, gh, gw, total4, rps);
-  else if (out_type == DT_F16) patchify_kernel<InT, __half><<<grid, threads, 0, stream>>>(in, static_cast<__half*>(out), B, H, W, C, P, gh, gw, total4, rps);
-  else patchify_kernel<InT, __nv_bfloat16><<<grid, threads, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), B, H, W, C, P, gh, gw, total4, rps);
+  for (int b0 = 0; b0 < B; b0 += 65535) {  // grid.y limit
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    const dim3 grid(static_cast<unsigned>((per_img4 + threads - 1) / threads), static_cast<unsigned>(nb));
+    const InT* src = in + static_cast<size_t>(b0) * H * W * C;
+    const size_t ooff = static_cast<size_t>(b0) * rps * P * P * C;
+    if (out_type == DT_F32) patchify_kernel<InT, float><<<grid, threads, 0, stream>>>(src, static_cast<float*>(out) + ooff, nb, H, W, C, P, gh, gw, per_img4, rps);
+    else if (out_type == DT_TF32) patchify_kernel<InT, tf32_t><<<grid, threads, 0, stream>>>(src, static_cast<tf32_t*>(out) + ooff, nb, H, W, C, P, gh, gw, per_img4, rps);
+    else if (out_type == DT_F16) patchify_kernel<InT, __half><<<grid, threads, 0, stream>>>(src, static_cast<__half*>(out) + ooff, nb, H, W, C, P, gh, gw, per_img4, rps);
+    else patchify_kernel<InT, __nv_bfloat16><<<grid, threads, 0, stream>>>(src, static_cast<__nv_bfloat16*>(out) + ooff, nb, H, W, C, P, gh, gw, per_img4, rps);
+  }
   JIMM_LAUNCH_CHECK();
   return 0;
 }
