@@ -31,6 +31,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace jimm {
@@ -77,6 +79,13 @@ struct EpiDev {
   // few of the CTA pairs.  When tail * parts <= #pairs those tiles are cut into `parts` (2 or 4) column slices of 256 / parts columns,
   // so the last round takes ~1 / parts of a round: virtual tiles [0, full) are whole tiles, [full, full + tail * parts) the slices.
   int full_tiles, tail_parts;
+  // fused LayerNorm of completed row groups (see GemmEpilogue)
+  const float* ln_scale;
+  const float* ln_bias;
+  void* ln_out;
+  int* ln_cnt;
+  int ln_out_type, ln_ldo;
+  float ln_eps;
   int vec;  // 1: N / ldo / ldr multiples of 4 and 16-byte aligned pointers -> vector accesses allowed (generic path)
 };
 
@@ -142,6 +151,91 @@ struct Traits<float> {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
+// ---- fused LayerNorm of a completed 32-row group (one warp) ----------------------------------------------------------------------
+// x rows are read back from L2 (they were just reduce-added there), two passes per row (statistics, then normalise; the second pass
+// hits L1), a few rows in flight per iteration.  Same arithmetic as layernorm_kernel (elementwise.cu): fp32, var = max(0, E[x^2] - E[x]^2).
+template <typename OutT>
+__device__ __forceinline__ void ln_rows_typed(const EpiDev& e, int row0, int lane) {
+  const int D = e.N, nv = D >> 7;  // float4 per lane per row (D is a multiple of 128 when nv * 128 == D; a remainder is handled below)
+  const int rem4 = (D >> 2) - nv * 32;  // leftover float4 of the row (D % 128 != 0): lanes [0, rem4)
+  const float inv_d = 1.0f / static_cast<float>(D);
+  const float4* sc = reinterpret_cast<const float4*>(e.ln_scale);
+  const float4* bi = reinterpret_cast<const float4*>(e.ln_bias);
+  const float* xbase = static_cast<const float*>(e.out);
+  const int rows = min(32, e.M - row0);
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += 4) {
+    float s[4], s2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // pass 1: four rows' loads in flight
+      s[i] = 0.f; s2[i] = 0.f;
+      if (r0 + i < rows) {
+        const float4* xr = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(row0 + r0 + i) * e.ldo);
+        for (int j = 0; j < nv; ++j) {
+          const float4 v = xr[lane + 32 * j];
+          s[i] += v.x + v.y + v.z + v.w;
+          s2[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        if (lane < rem4) {
+          const float4 v = xr[nv * 32 + lane];
+          s[i] += v.x + v.y + v.z + v.w;
+          s2[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r0 + i >= rows) break;
+      const float sum = warp_sum(s[i]), sum2 = warp_sum(s2[i]);
+      const float mean = sum * inv_d;
+      const float rstd = rsqrtf(fmaxf(sum2 * inv_d - mean * mean, 0.0f) + e.ln_eps);
+      const size_t row = static_cast<size_t>(row0 + r0 + i);
+      const float4* xr = reinterpret_cast<const float4*>(xbase + row * e.ldo);
+      OutT* orow = static_cast<OutT*>(e.ln_out) + row * e.ln_ldo;
+      const int nq = nv + (lane < rem4 ? 1 : 0);
+      for (int j = 0; j < nq; ++j) {
+        const int idx = lane + 32 * j;
+        const float4 v = xr[idx], g = __ldg(sc + idx), b = __ldg(bi + idx);
+        float4 y;
+        y.x = (v.x - mean) * rstd * g.x + b.x;
+        y.y = (v.y - mean) * rstd * g.y + b.y;
+        y.z = (v.z - mean) * rstd * g.z + b.z;
+        y.w = (v.w - mean) * rstd * g.w + b.w;
+        if constexpr (std::is_same<OutT, tf32_t>::value) {
+          reinterpret_cast<float4*>(orow)[idx] = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
+        } else {
+          uint2 pk;
+          constexpr int ot = std::is_same<OutT, __half>::value ? 1 : 2;
+          pk.x = pack2(y.x, y.y, ot);
+          pk.y = pack2(y.z, y.w, ot);
+          reinterpret_cast<uint2*>(orow)[idx] = pk;
+        }
+      }
+    }
+  }
+}
+
+// This warp's reduce-adds of `cols` columns into row group `rg` (32 rows) have been ISSUED; wait for their completion, publish, and if
+// that completes the rows (all N columns added, by whichever CTAs handled the other column tiles) normalise them.
+__device__ __noinline__ void ln_signal(const EpiDev& e, int rg, int cols, int lane) {
+  int last = 0;
+  if (lane == 0) {
+    tma_store_wait_all();   // the bulk reduce-adds of this thread are complete (performed in L2) ...
+    __threadfence();        // ... and ordered before the counter update (release; cumulative over what this thread observed)
+    const int old = atomicAdd(e.ln_cnt + rg, cols);
+    last = (old + cols == e.N) ? 1 : 0;
+    if (last) {
+      e.ln_cnt[rg] = 0;     // self-cleaning for the next launch
+      __threadfence();      // acquire side: the other contributors' adds are visible to the loads below
+    }
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  if (e.ln_out_type == DT_F16) ln_rows_typed<__half>(e, rg * 32, lane);
+  else if (e.ln_out_type == DT_BF16) ln_rows_typed<__nv_bfloat16>(e, rg * 32, lane);
+  else ln_rows_typed<tf32_t>(e, rg * 32, lane);
+}
+
 // ---- TMA epilogue for one 128 x 128 half-tile owned by one epilogue warp's lane quarter (thread = row) ------------
 // 16-bit outputs: 64 columns per 32 x 128 B box (two x32 TMEM loads); 32-bit outputs: 32 columns per box.
 // `release()` hands the accumulator back to the MMA issuer; it is called as soon as this warp's LAST tcgen05.ld has completed, i.e.
@@ -166,7 +260,14 @@ __device__ __forceinline__ void epilogue_tma(const CUtensorMap* map_c, const Epi
     else if (!more) { release(); released = true; }
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + j);
+      float4 b4;
+      if constexpr (OUT == OUT_F32_ADD) {
+        // straight from global (warp-uniform address, L1 broadcast): the residual epilogue has no per-tile bias staging and therefore no
+        // CTA-wide barrier -- its warps run independently, one of them may be normalising a finished row group (ln_signal)
+        b4 = (sbias != nullptr && n_tile0 + c + j < N) ? __ldg(reinterpret_cast<const float4*>(sbias + n_tile0 + c + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        b4 = *reinterpret_cast<const float4*>(sbias + c + j);
+      }
       const float v0 = act_ct<ACT>(__uint_as_float(r[j]) + b4.x), v1 = act_ct<ACT>(__uint_as_float(r[j + 1]) + b4.y);
       const float v2 = act_ct<ACT>(__uint_as_float(r[j + 2]) + b4.z), v3 = act_ct<ACT>(__uint_as_float(r[j + 3]) + b4.w);
       if constexpr (OUT16) {
@@ -472,6 +573,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int half = (warp_idx - 4) >> 2;  // column half of the 256-wide accumulator this warp drains
     int acc = 0;
     uint32_t acc_phase = 0, box_count = 0;
+    int ln_rg = -1, ln_cols = 0;  // row group / column count of this warp's previous tile, not yet published (fused LayerNorm)
     const uint32_t tmem_empty_leader0 = PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const TileCoord tc = decode_tile(epi, epi.reverse ? num_tiles - 1 - tile : tile, n_tiles);
@@ -479,7 +581,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int n_tile0 = tc.n_blk * BN + tc.n_off;  // first column of this (possibly sliced) tile
       const int c_len = tc.width / 2;                // accumulator columns per column half
       const int row_base = m_blk * TILE_M + static_cast<int>(cta_rank) * BM + q * 32;
-      if constexpr (OUT != OUT_GENERIC) {
+      if constexpr (OUT != OUT_GENERIC && OUT != OUT_F32_ADD) {
         // per-tile bias copy (one coalesced 128-bit load per lane of two warps), overlapped with the wait for the MMAs
         named_bar_sync(1, EPI_WARPS * 32);  // every epilogue warp is done with the previous tile's bias
         if (q == 0) {  // sbias[c] = bias[n_tile0 + c] for the accumulator columns c of this half
@@ -505,17 +607,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (dbg_no_epi) {
         release();
       } else if constexpr (OUT != OUT_GENERIC) {
-        if (row_base < M)
-          epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES, lane, row_base, n_tile0,
-                                           half * c_len, c_len, box_count, release);
-        else
+        if (row_base < M) {
+          epilogue_tma<OUT, ACT, EPI_BUFS>(&map_c, epi, taddr, OUT == OUT_F32_ADD ? epi.bias : sbias, epi_stage + (warp_idx - 4) * EPI_BUFS * EPI_BUF_BYTES,
+                                           lane, row_base, n_tile0, half * c_len, c_len, box_count, release);
+          if constexpr (OUT == OUT_F32_ADD) {
+            if (epi.ln_cnt) {
+              // Fused LayerNorm, deferred by one tile: the PREVIOUS tile's reduce-adds were issued a whole mainloop ago, so waiting for
+              // them costs nothing; this tile's accumulator has already been handed back, so the MMA issuer is not held up either.
+              if (ln_rg >= 0) ln_signal(epi, ln_rg, ln_cols, lane);
+              const int cols = min(c_len, N - (n_tile0 + half * c_len));
+              ln_rg = cols > 0 ? row_base >> 5 : -1;
+              ln_cols = cols;
+            }
+          }
+        } else {
           release();
+        }
       } else {
         if (half == 0 && row_base < M)
           epilogue_generic(epi, taddr, reinterpret_cast<float*>(epi_stage) + q * 32 * EPI_PITCH, lane, row_base, n_tile0);
         release();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (OUT == OUT_F32_ADD) {
+      if (epi.ln_cnt && ln_rg >= 0) ln_signal(epi, ln_rg, ln_cols, lane);
     }
     if constexpr (OUT != OUT_GENERIC) {
       if (lane == 0) tma_store_wait_all();
@@ -698,6 +814,8 @@ static EpiDev to_dev(const GemmEpilogue& e, int M, int N) {
   d.reverse = e.reverse;
   d.full_tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);  // overwritten by the pair-mode launch (its row blocks are 2 * BM)
   d.tail_parts = 1;
+  d.ln_scale = e.ln_scale; d.ln_bias = e.ln_bias; d.ln_out = e.ln_out; d.ln_cnt = nullptr;  // enabled by the pair-mode launch only
+  d.ln_out_type = e.ln_out_type; d.ln_ldo = e.ln_ldo; d.ln_eps = e.ln_eps;
   d.vec = epi_vec_ok(e, N);
   static int dbg = -1;
   if (dbg < 0) { const char* env = getenv("JIMM_GEMM_DEBUG"); dbg = env ? atoi(env) : 0; }
@@ -738,6 +856,7 @@ static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
     }
     d.full_tiles = parts > 1 ? tiles - tail : tiles;
     d.tail_parts = parts;
+    if (OUT == OUT_F32_ADD && p->epi.ln_cnt && p->epi.tok_pad == 0) d.ln_cnt = p->epi.ln_cnt;
     const int vtiles = d.full_tiles + (tiles - d.full_tiles) * parts;
     const int pairs = vtiles < max_pairs ? vtiles : max_pairs;
     JIMM_CUDA_CHECK(launch_k(gemm_tcgen05_kernel<T, OUT, ACT, true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, 2, true,
@@ -773,6 +892,12 @@ static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
     case DT_TF32: return launch_act<T, OUT_TF32>(p, M, stream);
     default: return launch_act<T, OUT_F32>(p, M, stream);
   }
+}
+
+// Will gemm_plan_run(p, M) normalise the finished rows itself (GemmEpilogue::ln_*)?  Same predicate as launch_one.
+int gemm_fuses_ln(const GemmPlan* p, int M_override) {
+  const int M = (M_override > 0 && M_override <= p->M) ? M_override : p->M;
+  return p->epi.ln_cnt != nullptr && p->epi.mode == 2 && p->epi.residual != nullptr && p->epi.tok_pad == 0 && pair_mode_enabled() && M >= 512;
 }
 
 int gemm_plan_run(const GemmPlan* p0, int M_override, cudaStream_t stream, int reverse) {
