@@ -152,55 +152,54 @@ struct Traits<float> {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- fused LayerNorm of a completed 32-row group (one warp) ----------------------------------------------------------------------
-// x rows are read back from L2 (they were just reduce-added there), two passes per row (statistics, then normalise; the second pass
-// hits L1), a few rows in flight per iteration.  Same arithmetic as layernorm_kernel (elementwise.cu): fp32, var = max(0, E[x^2] - E[x]^2).
-template <typename OutT>
-__device__ __forceinline__ void ln_rows_typed(const EpiDev& e, int row0, int lane) {
-  const int D = e.N, nv = D >> 7;  // float4 per lane per row (D is a multiple of 128 when nv * 128 == D; a remainder is handled below)
-  const int rem4 = (D >> 2) - nv * 32;  // leftover float4 of the row (D % 128 != 0): lanes [0, rem4)
-  const float inv_d = 1.0f / static_cast<float>(D);
+// The rows are read back from L2 (they were just reduce-added there).  What matters is bytes in flight: a batch of R rows (R * NV = up to 16
+// float4 per lane, all loads issued back to back) is normalised while the NEXT batch's loads are already outstanding (two register buffers);
+// the first version looped over a run-time number of float4 per row, the compiler serialised the loads, and a row group took ~60 us.
+// Same arithmetic as layernorm_kernel (elementwise.cu): fp32, var = max(0, E[x^2] - E[x]^2).  NV = D / 128 float4 per lane per row.
+template <typename OutT, int NV>
+__device__ __forceinline__ void ln_rows_nv(const EpiDev& e, int row0, int lane) {
+  constexpr int R = (16 / NV) > 0 ? (16 / NV) : 1;  // rows per batch
+  const float inv_d = 1.0f / static_cast<float>(NV * 128);
   const float4* sc = reinterpret_cast<const float4*>(e.ln_scale);
   const float4* bi = reinterpret_cast<const float4*>(e.ln_bias);
   const float* xbase = static_cast<const float*>(e.out);
   const int rows = min(32, e.M - row0);
-#pragma unroll 1
-  for (int r0 = 0; r0 < rows; r0 += 4) {
-    float s[4], s2[4];
+  float4 a[R][NV], b[R][NV];
+  auto load = [&](float4 (&buf)[R][NV], int r0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {  // pass 1: four rows' loads in flight
-      s[i] = 0.f; s2[i] = 0.f;
+    for (int i = 0; i < R; ++i) {
       if (r0 + i < rows) {
         const float4* xr = reinterpret_cast<const float4*>(xbase + static_cast<size_t>(row0 + r0 + i) * e.ldo);
-        for (int j = 0; j < nv; ++j) {
-          const float4 v = xr[lane + 32 * j];
-          s[i] += v.x + v.y + v.z + v.w;
-          s2[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-        if (lane < rem4) {
-          const float4 v = xr[nv * 32 + lane];
-          s[i] += v.x + v.y + v.z + v.w;
-          s2[i] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
+#pragma unroll
+        for (int j = 0; j < NV; ++j) buf[i][j] = xr[lane + 32 * j];
       }
     }
+  };
+  auto process = [&](float4 (&buf)[R][NV], int r0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < R; ++i) {
       if (r0 + i >= rows) break;
-      const float sum = warp_sum(s[i]), sum2 = warp_sum(s2[i]);
-      const float mean = sum * inv_d;
-      const float rstd = rsqrtf(fmaxf(sum2 * inv_d - mean * mean, 0.0f) + e.ln_eps);
-      const size_t row = static_cast<size_t>(row0 + r0 + i);
-      const float4* xr = reinterpret_cast<const float4*>(xbase + row * e.ldo);
-      OutT* orow = static_cast<OutT*>(e.ln_out) + row * e.ln_ldo;
-      const int nq = nv + (lane < rem4 ? 1 : 0);
-      for (int j = 0; j < nq; ++j) {
+      float s = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 v = buf[i][j];
+        s += v.x + v.y + v.z + v.w;
+        s2 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      }
+      s = warp_sum(s);
+      s2 = warp_sum(s2);
+      const float mean = s * inv_d;
+      const float rstd = rsqrtf(fmaxf(s2 * inv_d - mean * mean, 0.0f) + e.ln_eps);
+      OutT* orow = static_cast<OutT*>(e.ln_out) + static_cast<size_t>(row0 + r0 + i) * e.ln_ldo;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
         const int idx = lane + 32 * j;
-        const float4 v = xr[idx], g = __ldg(sc + idx), b = __ldg(bi + idx);
+        const float4 v = buf[i][j], g = __ldg(sc + idx), bb = __ldg(bi + idx);
         float4 y;
-        y.x = (v.x - mean) * rstd * g.x + b.x;
-        y.y = (v.y - mean) * rstd * g.y + b.y;
-        y.z = (v.z - mean) * rstd * g.z + b.z;
-        y.w = (v.w - mean) * rstd * g.w + b.w;
+        y.x = (v.x - mean) * rstd * g.x + bb.x;
+        y.y = (v.y - mean) * rstd * g.y + bb.y;
+        y.z = (v.z - mean) * rstd * g.z + bb.z;
+        y.w = (v.w - mean) * rstd * g.w + bb.w;
         if constexpr (std::is_same<OutT, tf32_t>::value) {
           reinterpret_cast<float4*>(orow)[idx] = make_float4(round_tf32(y.x), round_tf32(y.y), round_tf32(y.z), round_tf32(y.w));
         } else {
@@ -212,6 +211,33 @@ __device__ __forceinline__ void ln_rows_typed(const EpiDev& e, int row0, int lan
         }
       }
     }
+  };
+  load(a, 0);
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += 2 * R) {
+    load(b, r0 + R);
+    process(a, r0);
+    load(a, r0 + 2 * R);
+    process(b, r0 + R);
+  }
+}
+
+template <typename OutT>
+__device__ __forceinline__ void ln_rows_typed(const EpiDev& e, int row0, int lane) {
+  switch (e.N >> 7) {  // the host only enables the fused path for N % 128 == 0, N <= 2048
+    case 1: ln_rows_nv<OutT, 1>(e, row0, lane); break;
+    case 2: ln_rows_nv<OutT, 2>(e, row0, lane); break;
+    case 3: ln_rows_nv<OutT, 3>(e, row0, lane); break;
+    case 4: ln_rows_nv<OutT, 4>(e, row0, lane); break;
+    case 5: ln_rows_nv<OutT, 5>(e, row0, lane); break;
+    case 6: ln_rows_nv<OutT, 6>(e, row0, lane); break;
+    case 7: ln_rows_nv<OutT, 7>(e, row0, lane); break;
+    case 8: ln_rows_nv<OutT, 8>(e, row0, lane); break;
+    case 9: ln_rows_nv<OutT, 9>(e, row0, lane); break;
+    case 10: ln_rows_nv<OutT, 10>(e, row0, lane); break;
+    case 12: ln_rows_nv<OutT, 12>(e, row0, lane); break;
+    case 16: ln_rows_nv<OutT, 16>(e, row0, lane); break;
+    default: break;
   }
 }
 
@@ -856,7 +882,7 @@ static int launch_one(const GemmPlan* p, int M, cudaStream_t stream) {
     }
     d.full_tiles = parts > 1 ? tiles - tail : tiles;
     d.tail_parts = parts;
-    if (OUT == OUT_F32_ADD && p->epi.ln_cnt && p->epi.tok_pad == 0) d.ln_cnt = p->epi.ln_cnt;
+    if (OUT == OUT_F32_ADD && gemm_fuses_ln(p, M)) d.ln_cnt = p->epi.ln_cnt;
     const int vtiles = d.full_tiles + (tiles - d.full_tiles) * parts;
     const int pairs = vtiles < max_pairs ? vtiles : max_pairs;
     JIMM_CUDA_CHECK(launch_k(gemm_tcgen05_kernel<T, OUT, ACT, true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, stream, 2, true,
@@ -897,7 +923,9 @@ static int launch_tc(const GemmPlan* p, int M, cudaStream_t stream) {
 // Will gemm_plan_run(p, M) normalise the finished rows itself (GemmEpilogue::ln_*)?  Same predicate as launch_one.
 int gemm_fuses_ln(const GemmPlan* p, int M_override) {
   const int M = (M_override > 0 && M_override <= p->M) ? M_override : p->M;
-  return p->epi.ln_cnt != nullptr && p->epi.mode == 2 && p->epi.residual != nullptr && p->epi.tok_pad == 0 && pair_mode_enabled() && M >= 512;
+  const int nv = p->N >> 7;
+  const bool width_ok = p->N % 128 == 0 && (nv <= 10 || nv == 12 || nv == 16);  // ln_rows_typed's instantiations
+  return p->epi.ln_cnt != nullptr && width_ok && p->epi.mode == 2 && p->epi.residual != nullptr && p->epi.tok_pad == 0 && pair_mode_enabled() && M >= 512;
 }
 
 int gemm_plan_run(const GemmPlan* p0, int M_override, cudaStream_t stream, int reverse) {
