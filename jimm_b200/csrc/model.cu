@@ -233,7 +233,10 @@ struct jimm_model {
   int epi_mode_16 = 2;  // epilogue mode for 16-bit no-residual outputs (2 = TMA store)
   int epi_mode_res = 2; // epilogue mode for fp32 residual outputs (2 = TMA reduce-add into the residual stream)
   bool l2_alternate = true;  // JIMM_L2_ALTERNATE=0 disables the alternating walk direction
-  bool fuse_ln = true;       // JIMM_FUSE_LN=0: LayerNorm stays a kernel (A/B, bisection)
+  // JIMM_FUSE_LN=1: the out-proj / FC2 GEMMs normalise the rows they complete (gemm.cu, "fused LayerNorm").  Off by default: it removes
+  // two launches per block but is SLOWER on every measured shape (14.1 vs 11.5 ms/step, ViT-B/16 B=256) -- the row read-back competes with
+  // the GEMM's own TMA traffic for the SM<->L2 ports that already bound it.  Kept for A/B runs and covered by tests.
+  bool fuse_ln = false;
   bool simt = false;    // JIMM_GEMM_IMPL=simt: bisection aid, routes every GEMM through the SIMT cross-check kernel
   // CUDA-graph replay of a whole tower for small batches (launch-bound regime; config 1 is B=4): the second call of a
   // (tower, batch, dtype | length) shape is stream-captured from fixed staging buffers, later calls replay it.
