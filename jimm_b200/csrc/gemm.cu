@@ -149,7 +149,6 @@ struct Traits<float> {
   static constexpr int KIND = 1, FMT = 2;
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 // ---- fused LayerNorm of completed 32-row groups (CTA-pair reduce-add epilogue) -----------------------------------------------------
 // Who normalises: NOT the epilogue warps.  A first version let the epilogue warp that completed a row group normalise it in place; every
@@ -819,6 +818,22 @@ int make_tensor_map_3d(CUtensorMap* map, int dtype, const void* ptr, int B, int 
   CUresult r = enc(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", static_cast<int>(r)); return -3; }
+  return 0;
+}
+// [B, S, N] view with a 32-row x 64-byte box (SWIZZLE_64B): the per-warp output box of the column-split attention kernel
+int make_tensor_map_3d_box64(CUtensorMap* map, int dtype, const void* ptr, int B, int S, int N, int ld) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return -3;
+  const size_t es = dtype_size(dtype);
+  CUtensorMapDataType dt = (dtype == DT_F32 || dtype == DT_TF32) ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                           : (dtype == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(ld) * es, static_cast<cuuint64_t>(S) * ld * es};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(64 / es), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, dt, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled(3d, 64 B box) failed: CUresult %d", static_cast<int>(r)); return -3; }
   return 0;
 }
 static int make_map_3d_f32(CUtensorMap* map, const void* ptr, int B, int S, int N, int ld) { return make_tensor_map_3d(map, DT_F32, ptr, B, S, N, ld); }
