@@ -436,14 +436,8 @@ static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int
 }
 
 // Returns 1 when this configuration is not handled here (caller falls back to attention.cu / attention_tc_long.cu).
-int attention_tc_split_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse);  // attention_tc_split.cu
 int attention_tc_run(const void* qkv, int io_type, void* out, int out_type, int B, int S, int H, int causal, cudaStream_t stream, int reverse) {
   if (S > 256 || S < 1) return 1;
-  {
-    static int split = -1;  // JIMM_ATTN_SPLIT=1: the two-threads-per-row variant (A/B runs; see profiles/r2_b_attention.md)
-    if (split < 0) { const char* env = getenv("JIMM_ATTN_SPLIT"); split = env ? atoi(env) : 0; }
-    if (split) return attention_tc_split_run(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
-  }
   if ((reinterpret_cast<uintptr_t>(qkv) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) return 1;
   if (io_type == DT_F16 && out_type == DT_F16) return atc_launch<__half, __half>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);
   if (io_type == DT_F16 && out_type == DT_F32) return atc_launch<__half, float>(qkv, io_type, out, out_type, B, S, H, causal, stream, reverse);

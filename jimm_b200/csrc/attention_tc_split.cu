@@ -27,7 +27,6 @@
 // The two halves of a row need ONE reference maximum: they swap the maxima of their first chunks through shared memory (bf16 -- the
 // reference only has to be common and within 2^8 of the true maximum), raise it lazily as before, and reconcile the rare divergence at the
 // end when they swap (m_ref, l) through tensor memory.
-#include <cstdio>
 #include <type_traits>
 
 #include "common.cuh"
@@ -148,15 +147,10 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
       const uint32_t idesc_qk = make_idesc(FMT, 128, static_cast<uint32_t>(p.Nk), 0);
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
       const int nkk = p.Nk / 16;
-      const bool trace = (p.debug & 8) != 0 && blockIdx.x == 0;  // JIMM_ATC_DEBUG=8: cycle breakdown of CTA 0 (printf at exit)
-      long long tw_pready = 0, tw_kv = 0, tw_slot = 0;
-      const long long t_begin = trace ? clock64() : 0;
       // P V of unit v (slot v & 1, k-th use of that slot k = v >> 1), reading V from item buffer vbuf; `last` = last unit of its item
       auto issue_pv = [&](int v, int vbuf, bool last) {
         const int g = v & 1;
-        const long long tp0 = trace ? clock64() : 0;
         mbar_wait(&p_ready[g], static_cast<uint32_t>(v >> 1) & 1u);
-        if (trace) tw_pready += clock64() - tp0;
         tcgen05_fence_after();
         if (leader) {
           const uint64_t vdesc = make_umma_desc_sw128(smem_u32(smem + vbuf * item_bytes + 2 * tile_bytes));
@@ -174,15 +168,11 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
         const uint32_t q_addr = smem_u32(smem + buf * item_bytes);
         // descriptors advance by (bytes >> 4) in their address field: 32 B per 16-element K step, 2048 B per 16 keys of V
         const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + tile_bytes);
-        const long long tk0 = trace ? clock64() : 0;
         mbar_wait(&kv_full[buf], ph);
-        if (trace) tw_kv += clock64() - tk0;
         tcgen05_fence_after();
         for (int t = 0; t < p.nq; ++t, ++un) {
           const int g = un & 1;
-          const long long ts0 = trace ? clock64() : 0;
           mbar_wait(&slot_free[g], (static_cast<uint32_t>(un >> 1) & 1u) ^ 1u);  // the previous unit of this slot has been read out
-          if (trace) tw_slot += clock64() - ts0;
           tcgen05_fence_after();
           if (leader) {
 #pragma unroll
@@ -198,10 +188,6 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
         if (++buf == p.nbuf) { buf = 0; ph ^= 1; }
       }
       if (un > 0) issue_pv(un - 1, prev_buf, prev_last);
-      if (trace && lane == 0)
-        printf("atc issuer: units %d total %lld clk; waiting p_ready %lld, kv_full %lld, slot_free %lld (per unit %lld / %lld / %lld / %lld)\n", un,
-               clock64() - t_begin, tw_pready, tw_kv, tw_slot, (clock64() - t_begin) / max(un, 1), tw_pready / max(un, 1), tw_kv / max(un, 1),
-               tw_slot / max(un, 1));
     }
   } else {
     // ===================== softmax + output =====================
@@ -220,9 +206,6 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
       // exchange columns: right behind each half's P region (its own consumed score columns)
       const int xa_col = 16 * nA, xb_col = 32 * nA + 16 * (n_chunks - nA);
       const bool peer_has = ch == 0 ? (n_chunks > nA) : true;  // half B is empty when the keys fit one chunk
-      const bool trace = (p.debug & 8) != 0 && blockIdx.x == 0 && q == 0;
-      long long tw_s = 0, t_soft = 0, tw_x1 = 0, tw_x2 = 0, tw_o = 0, t_out = 0;
-      int traced = 0;
       for (int un = g; un < my_units; un += 2) {
         const int it = p.nq == 2 ? un >> 1 : un, t = p.nq == 2 ? un & 1 : 0;
         const int item = static_cast<int>(blockIdx.x) + it * static_cast<int>(gridDim.x);
@@ -236,9 +219,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
         const int kmax_warp = CAUSAL ? min(S, t * 128 + q * 32 + 32) : S;
         const int kmin_warp = CAUSAL ? min(S, t * 128 + q * 32 + 1) : S;  // keys valid for EVERY lane of this warp
         const int n_live = min(c1, (kmax_warp + 31) / 32), n_full = kmin_warp / 32;  // this half: chunks [c0, n_live) carry keys
-        long long tc = trace ? clock64() : 0;
         mbar_wait(&s_full[g], sp);
-        if (trace) { const long long n = clock64(); tw_s += n - tc; tc = n; ++traced; }
         tcgen05_fence_after();
         if (t * 128 + q * 32 >= S) {
           // No query row of this warp pair exists (S = 197: rows 224..255 of the second tile; S = 50: the upper two quarters): keep the
@@ -296,9 +277,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
         }
         const __nv_bfloat16 mine16 = __float2bfloat16_rn(cm_first);
         *xmine = mine16;
-        long long tb = trace ? clock64() : 0;
         named_bar_sync(pair_bar, 64);
-        if (trace) tw_x1 += clock64() - tb;
         float m_ref = fmaxf(__bfloat162float(mine16), __bfloat162float(*xpeer));  // finite: key 0 is valid for every row
         const float m_ref0 = m_ref;
         // One chunk = 32 scores of the row.  Short dependent chains (four interleaved max / sum chains) and the exponentials issued
@@ -398,9 +377,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
           tmem_st_32x32b_x2(taddr + (ch == 0 ? xa_col : xb_col), __float_as_uint(m_ref), __float_as_uint(l));
         }
         tmem_st_wait();
-        tb = trace ? clock64() : 0;
         named_bar_sync(pair_bar, 64);
-        if (trace) tw_x2 += clock64() - tb;
         float pm = -INFINITY, pl = 0.f;
         if (peer_has) {
           uint32_t u0, u1;
@@ -435,9 +412,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
         if (lane == 0) mbar_arrive(&p_ready[g]);
         // ---- output: this half's 32 columns of O / l ----
         const float inv = 1.0f / l;
-        if (trace) { const long long n = clock64(); t_soft += n - tc; tc = n; }
         mbar_wait(&o_full[g], sp);
-        if (trace) { const long long n = clock64(); tw_o += n - tc; tc = n; }
         tcgen05_fence_after();
         if (!(p.debug & 4)) {
           tmem_ld_32x32b_x32(taddr + o_col + ch * 32, r);
@@ -477,12 +452,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap map_qkv, const __g
             }
           }
         }
-        if (trace) t_out += clock64() - tc;
       }
-      if (trace && lane == 0)
-        printf("atc softmax warp g=%d half=%d: units %d; per unit: wait s_full %lld, softmax %lld (of which pair barriers %lld + %lld), wait o_full %lld, output %lld\n",
-               g, ch, traced, tw_s / max(traced, 1), t_soft / max(traced, 1), tw_x1 / max(traced, 1), tw_x2 / max(traced, 1), tw_o / max(traced, 1),
-               t_out / max(traced, 1));
     }
   }
 

@@ -180,6 +180,22 @@ def test_attention_flash_kernel_forced(lib, monkeypatch, S, causal):
     assert rel_err(out, _attn_ref(qkv, B, S, H, causal)) < 3e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("S,causal", [(1, 0), (16, 1), (33, 0), (50, 0), (64, 1), (77, 1), (128, 0), (129, 1), (160, 0), (192, 1), (197, 0), (224, 0), (225, 1), (256, 0), (256, 1)])
+def test_attention_split_variant(lib, monkeypatch, dtype, S, causal):
+    """JIMM_ATTN_IMPL=split: the two-threads-per-row variant of the S <= 256 tcgen05 kernel (slower, kept for A/B runs;
+    profiles/r2_b_attention.md) -- every chunk split nA/nB = 1/0 .. 4/4, both output widths, more items than SMs."""
+    monkeypatch.setenv("JIMM_ATTN_IMPL", "split")
+    B, H = 30, 6
+    qkv = (torch.randn(B * S, 3 * H * 64, device=DEV) * 1.5).to(dtype)
+    ref = _attn_ref(qkv, B, S, H, causal)
+    tol = 3e-3 if dtype == torch.float16 else 2e-2
+    for out_dtype in (dtype, torch.float32):
+        out = torch.empty(B * S, H * 64, dtype=out_dtype, device=DEV)
+        check(lib, lib.jimm_k_attention(ptr(qkv), CODE[dtype], ptr(out), CODE[out_dtype], B, S, H, causal, stream()))
+        assert rel_err(out, ref) < tol, (S, causal, out_dtype, rel_err(out, ref))
+
+
 def test_attention_many_items_persistent(lib):
     """More (sample, head) items than SMs: exercises the persistent loop, the 2-deep smem ring and TMEM slot reuse."""
     B, S, H = 40, 197, 12
