@@ -397,7 +397,7 @@ def collective_leg(args, rank, world, local, lib):
     import torch
     import torch.distributed as dist
 
-    wl = "siglip2_l16_512" if world >= 8 else "clip_b32"
+    wl = os.environ.get("JIMM_BENCH_COLLECTIVE_WL") or ("siglip2_l16_512" if world >= 8 else "clip_b32")  # (override: dry-run the c5 leg on fewer GPUs)
     steps = max(2, min(args.steps, 3 if wl == "siglip2_l16_512" else 10))
     bw = Bench(wl, 0, rank, world, local, lib)
     m, B = bw.model, bw.B
