@@ -50,7 +50,7 @@ comm_logits_kernel(CommPtrs ptrs, const float* __restrict__ img_e, const float* 
                    int world, unsigned int epoch, unsigned int* counter, const float* __restrict__ logit_scale,
                    const float* __restrict__ logit_bias, float* __restrict__ logits_local, unsigned long long timeout_ns,
                    unsigned int* status /* host-mapped */) {
-  __shared__ float As[16][65], Bs[16][65];
+  __shared__ __align__(16) float As[16][LOGITS_LDS], Bs[16][LOGITS_LDS];
   __shared__ int s_last;
   __shared__ unsigned int s_err;
   if (threadIdx.x == 0) s_err = 0u;
@@ -145,8 +145,8 @@ int comm_init(CommState* c, int rank, int world, int max_rows, int E, unsigned c
   for (int i = 0; i < kMaxWorld; ++i) c->peer_base[i] = nullptr;
   c->peer_base[rank] = c->base;
   c->local_buf = static_cast<float*>(c->base);
+  // One CTA per SM: BASELINE configs[4] is 128 logits tiles per rank (64 CTAs took two rounds and lost to the NCCL path, r2_bench_n8).
   c->grid = device_sm_count();
-  if (c->grid > 64) c->grid = 64;  // tiny op: 64 CTAs cover the row scatter and the logits tiles
   // A CTA that is not resident yet (the SMs still hold the previous kernel) only delays the last-CTA ticket; the resident ones spin on
   // flags that depend on OTHER GPUs and on that ticket, never on a CTA that needs their SM to make room -- no co-residency assumption.
   JIMM_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&c->status_host), sizeof(unsigned int), cudaHostAllocMapped));

@@ -331,7 +331,7 @@ int l2_normalize_run(const float* x, float* out, int ldo, int B, int E, cudaStre
 __global__ void __launch_bounds__(256)
 logits_kernel(const float* __restrict__ img, const float* __restrict__ txt, const float* __restrict__ logit_scale,
               const float* __restrict__ logit_bias, float* __restrict__ out, int Bi, int Bt, int E, size_t ldl) {
-  __shared__ float As[16][65], Bs[16][65];
+  __shared__ __align__(16) float As[16][LOGITS_LDS], Bs[16][LOGITS_LDS];
   const float sc = expf(*logit_scale);
   const float bs = logit_bias ? *logit_bias : 0.f;
   logits_tile<false>(img, E, txt, E, out, ldl, Bi, Bt, E, blockIdx.y * 64, blockIdx.x * 64, sc, bs, As, Bs);
