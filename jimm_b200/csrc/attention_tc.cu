@@ -50,7 +50,6 @@ struct AtcParams {
   float scale_log2;
   void* out;
   int reverse;  // walk the (sample, head) items from the end (see kernels.cuh)
-  int poll;     // issuer serves whichever of {next Q K^T, next P V} is ready first instead of the fixed alternation (JIMM_ATC_POLL)
 };
 
 template <typename T, typename OutT, bool CAUSAL>
@@ -130,9 +129,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
       const uint32_t idesc_pv = make_idesc(FMT, 128, 64, 1);  // B = V is MN-major (keys are the strided dimension)
       const int nkk = p.Nk / 16;
       // P V of unit v (slot v & 1, k-th use of that slot k = v >> 1), reading V from item buffer vbuf; `last` = last unit of its item
-      auto issue_pv = [&](int v, int vbuf, bool last, bool wait = true) {
+      auto issue_pv = [&](int v, int vbuf, bool last) {
         const int g = v & 1;
-        if (wait) mbar_wait(&p_ready[g], static_cast<uint32_t>(v >> 1) & 1u);
+        mbar_wait(&p_ready[g], static_cast<uint32_t>(v >> 1) & 1u);
         tcgen05_fence_after();
         if (leader) {
           const uint64_t vdesc = make_umma_desc_sw128(smem_u32(smem + vbuf * item_bytes + 2 * tile_bytes));
@@ -143,52 +142,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           if (last) tcgen05_commit(&kv_empty[vbuf]);  // every MMA reading this item's smem has retired
         }
       };
-      if (p.poll) {
-        // Two independent streams (Q K^T of unit qn, P V of unit pn < qn) served in readiness order.  The fixed alternation below parks the
-        // issuer on slot_free of the NEXT unit (read-out of unit qn - 2 pending) while p_ready of the previous one has already arrived, and
-        // vice versa: the cycle counters of profiles/r2_b_attention.md show softmax warps waiting 1600-3000 clk for o_full.
-        int qn = 0, q_t = 0, q_buf = 0;       // next Q K^T: unit, query tile inside its item, item buffer
-        uint32_t q_ph = 0;
-        int pn = 0, p_t = 0, p_buf = 0;       // next P V
-        while (pn < my_units) {
-          bool did = false;
-          if (qn < my_units) {
-            const int g = qn & 1;
-            if (mbar_test_wait(&slot_free[g], (static_cast<uint32_t>(qn >> 1) & 1u) ^ 1u) && (q_t != 0 || mbar_test_wait(&kv_full[q_buf], q_ph))) {
-              tcgen05_fence_after();
-              if (leader) {
-                const uint32_t q_addr = smem_u32(smem + q_buf * item_bytes);
-                const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + tile_bytes);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_ss<0>(tmem_base + g * 256, qdesc + static_cast<uint64_t>(q_t * (16384 >> 4) + k * 2), kdesc + static_cast<uint64_t>(k * 2),
-                             idesc_qk, k > 0 ? 1u : 0u);
-                tcgen05_commit(&s_full[g]);
-              }
-              ++qn;
-              if (++q_t == p.nq) {
-                q_t = 0;
-                if (++q_buf == p.nbuf) { q_buf = 0; q_ph ^= 1; }
-              }
-              did = true;
-            }
-          }
-          if (pn < qn && mbar_test_wait(&p_ready[pn & 1], static_cast<uint32_t>(pn >> 1) & 1u)) {
-            issue_pv(pn, p_buf, p_t == p.nq - 1, false);
-            ++pn;
-            if (++p_t == p.nq) {
-              p_t = 0;
-              if (++p_buf == p.nbuf) p_buf = 0;
-            }
-            did = true;
-          }
-          if (!did) __nanosleep(20);
-        }
-      }
       int buf = 0, un = 0, prev_buf = 0;
       uint32_t ph = 0;
       bool prev_last = false;
-      for (int it = 0; it < (p.poll ? 0 : my_items); ++it) {
+      for (int it = 0; it < my_items; ++it) {
         const uint32_t q_addr = smem_u32(smem + buf * item_bytes);
         // descriptors advance by (bytes >> 4) in their address field: 32 B per 16-element K step, 2048 B per 16 keys of V
         const uint64_t qdesc = make_umma_desc_sw128(q_addr), kdesc = make_umma_desc_sw128(q_addr + tile_bytes);
@@ -465,11 +422,6 @@ static int atc_launch(const void* qkv, int io_type, void* out, int out_type, int
   p.scale_log2 = 0.125f * 1.4426950408889634f;
   p.out = out;
   p.reverse = reverse;
-  {
-    static int poll = -1;
-    if (poll < 0) { const char* env = getenv("JIMM_ATC_POLL"); poll = env ? atoi(env) : 0; }
-    p.poll = poll;
-  }
   const int items = B * H;
   const int grid = items < device_sm_count() ? items : device_sm_count();
   static DeviceOnce attr_set;
