@@ -146,9 +146,11 @@ int comm_init(CommState* c, int rank, int world, int max_rows, int E, unsigned c
   c->peer_base[rank] = c->base;
   c->local_buf = static_cast<float*>(c->base);
   // One CTA per SM: BASELINE configs[4] is 128 logits tiles per rank (64 CTAs took two rounds and lost to the NCCL path, r2_bench_n8).
+  // Every CTA must become resident for the rank to publish (the last-CTA ticket), and resident CTAs spin on the peers' flags: the grid has
+  // to fit the SMs that are free when the head runs.  At 95 registers x 256 threads and 8.7 KB of shared memory two CTAs fit one SM, so
+  // #SM CTAs need half the machine; the head is launched after the towers have joined, with nothing else in flight.  A launch that cannot
+  // become resident ends in the bounded wait's timeout (NaN logits + jimm_comm_status), not in a hang.
   c->grid = device_sm_count();
-  // A CTA that is not resident yet (the SMs still hold the previous kernel) only delays the last-CTA ticket; the resident ones spin on
-  // flags that depend on OTHER GPUs and on that ticket, never on a CTA that needs their SM to make room -- no co-residency assumption.
   JIMM_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&c->status_host), sizeof(unsigned int), cudaHostAllocMapped));
   *c->status_host = 0u;
   JIMM_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->status_dev), c->status_host, 0));
