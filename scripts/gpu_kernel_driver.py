@@ -71,6 +71,13 @@ def make():
         ie, te = torch.randn(256, 512, device=dev), torch.randn(256, 512, device=dev)
         keep.append((m, n))
         return (lambda: n.comm_logits(ie, te)), 2.0 * 256 * 256 * 512, 2 * 256 * 512 * 4 * 2
+    if name == "logits_c5":  # one rank's [256, 2048] x 1024 logits row block of BASELINE configs[4] (the shared fp32 tile, logits_tile.cuh)
+        Bi, Bt, E = 256, 2048, 1024
+        a = torch.nn.functional.normalize(torch.randn(Bi, E, device=dev), dim=-1)
+        b = torch.nn.functional.normalize(torch.randn(Bt, E, device=dev), dim=-1)
+        sc = torch.tensor([2.0], device=dev)
+        out = torch.empty(Bi, Bt, device=dev)
+        return (lambda: check(lib, lib.jimm_k_logits(ptr(a), ptr(b), ptr(sc), None, ptr(out), Bi, Bt, E, Bt, stream()))), 2.0 * Bi * Bt * E, (Bi + Bt) * E * 4 + Bi * Bt * 4
     raise SystemExit(f"unknown kernel {name}")
 
 

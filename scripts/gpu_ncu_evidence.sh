@@ -16,6 +16,7 @@ for k in ${KERNELS:-gemm_qkv gemm_fc1 gemm_fc2 gemm_out gemm_patch attn_197 attn
     patchify) pat="regex:patchify" ;;
     map_attention) pat="regex:map_attention" ;;
     comm_logits) pat="regex:comm_logits" ;;
+    logits_c5) pat="regex:logits_kernel" ;;
   esac
   timeout 300 ncu --metrics $M --clock-control none -k $pat -s 2 -c 1 --csv --log-file $OUT/$k.csv python scripts/gpu_kernel_driver.py $k 1 > $OUT/$k.log 2>&1
   echo "$k rc=$?"
