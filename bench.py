@@ -309,7 +309,12 @@ class Bench:
             self.ids_dev = self.ids_host.to(self.dev)
             self.step_dev = lambda: self.model(self.img_dev, self.ids_dev)
             self.step_host = lambda: self.model(self.img_host, self.ids_host)
-            self.step_host_u8 = None
+            # raw frames + token ids: what examples/clip_inference.py:35-38 hands its (host) processor; bytes over PCIe, front-end on the GPU
+            from jimm_b200.preprocess import ImagePreprocessor
+
+            self.u8_host = torch.randint(0, 256, (self.B, self.img_size, self.img_size, 3), generator=g, dtype=torch.uint8).pin_memory()
+            self.model.set_preprocessor(ImagePreprocessor.clip(self.img_size) if workload == "clip_b32" else ImagePreprocessor.siglip(self.img_size))
+            self.step_host_u8 = lambda: self.model(self.u8_host, self.ids_host)
         else:
             self.step_dev = lambda: self.model(self.img_dev)
             self.step_host = lambda: self.model(self.img_host)
@@ -371,9 +376,10 @@ class Bench:
         else:
             self.warm(self.step_host_u8)
             ms8, _ = self.timed(self.step_host_u8, steps)
-            out = {"value": self.rate(ms8, steps), "unit": "images/sec", "h2d_bytes_per_step": self.u8_host.numel(), "d2h_bytes_per_step": d2h,
+            out = {"value": self.rate(ms8, steps), "unit": "pairs/sec" if self.dual else "images/sec",
+                   "h2d_bytes_per_step": self.u8_host.numel() + (self.ids_host.numel() * 4 if self.dual else 0), "d2h_bytes_per_step": d2h,
                    "ms_per_step": ms8 / steps, "sync": "every step",
-                   "input": "pinned uint8 RGB frames; GPU image front-end (jimm_preproc_run) + tower inside the timed region",
+                   "input": "pinned uint8 RGB frames" + (" + int32 token ids" if self.dual else "") + "; GPU image front-end (jimm_preproc_run) + tower(s) inside the timed region",
                    "fp32_input": f32}
             if pipelined and hasattr(self.model, "forward_async"):
                 # the same loop with asynchronous dispatch, two calls in flight (every step still copies its inputs in and its result out)
@@ -406,8 +412,9 @@ def collective_leg(args, rank, world, local, lib):
         bw.step_dev()
     torch.cuda.synchronize(bw.dev)
     ms, out = bw.timed(bw.step_dev, steps)
-    bw.warm(bw.step_host)
-    ms_h, _ = bw.timed(bw.step_host, steps)
+    host_step = bw.step_host_u8 or bw.step_host  # raw uint8 frames + token ids when the front-end is attached
+    bw.warm(host_step)
+    ms_h, _ = bw.timed(host_step, steps)
     n = m.native(B, require=True)
     # ---- the collective kernel alone: encoder outputs resident, CUDA events around `reps` back-to-back calls (every call carries its
     #      own cross-GPU flag barrier, so the ranks run it in lock-step), max over ranks
@@ -465,7 +472,8 @@ def collective_leg(args, rank, world, local, lib):
                           "(models/clip.py:183-187, models/siglip.py:169-173, examples/clip_inference.py:41-44)",
         "value": bw.rate(ms, steps), "unit": "pairs/sec", "ms_per_step": ms / steps, "steps": steps,
         "e2e": {"value": bw.rate(ms_h, steps), "unit": "pairs/sec", "ms_per_step": ms_h / steps,
-                "h2d_bytes_per_step": bw.img_host.numel() * 4 + bw.ids_host.numel() * 4, "d2h_bytes_per_step": B * world * B * 4},
+                "h2d_bytes_per_step": (bw.u8_host.numel() if bw.step_host_u8 else bw.img_host.numel() * 4) + bw.ids_host.numel() * 4,
+                "d2h_bytes_per_step": B * world * B * 4, "input": "pinned uint8 RGB frames + int32 token ids" if bw.step_host_u8 else "pinned fp32 pixels + int32 token ids"},
         "us_per_call": us, "us_per_call_stat": "median of per-call CUDA-event times, max over ranks", "us_per_call_mean": ms_k / reps * 1e3,
         "us_per_call_min": us_min, "us_per_call_max": us_max, "calls_timed": reps, "bytes_sent_per_peer": bytes_per_peer, "peers": world - 1,
         "nvlink_egress_gbs": egress / (us * 1e-6) / 1e9, "nvlink_peak_gbs": 770.0, "nvlink_frac": egress / (us * 1e-6) / 1e9 / 770.0,

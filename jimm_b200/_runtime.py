@@ -179,7 +179,7 @@ class NativeModel:
                 if xd.dtype == torch.uint8:
                     xd = self.preproc(xd, dtype=self._operand_dtype())
                 od = torch.empty((B, self.vision_out), dtype=torch.float32, device=self.device)
-                _lib.check(fn_dev(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[x.dtype], B, C.c_void_p(od.data_ptr()),
+                _lib.check(fn_dev(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[xd.dtype], B, C.c_void_p(od.data_ptr()),
                                   C.c_void_p(_stream_ptr(self.device))))
                 out.copy_(od, non_blocking=True)
             else:
@@ -228,6 +228,21 @@ class NativeModel:
         ids = self._prep_ids(text)
         Bi, (Bt, T) = x.shape[0], ids.shape
         with torch.cuda.device(self.device):
+            if x.dtype == torch.uint8:
+                # raw RGB frames (model.set_preprocessor): bytes over PCIe, the image front-end on the GPU, then both towers concurrently
+                host_in = not x.is_cuda and not ids.is_cuda
+                xd = self.preproc(x.to(self.device, non_blocking=True), dtype=self._operand_dtype())
+                idd = ids.to(self.device, non_blocking=True)
+                out = torch.empty((Bi, Bt), dtype=torch.float32, device=self.device)
+                _lib.check(self.lib.jimm_dual_forward(self.handle, C.c_void_p(xd.data_ptr()), _TORCH_TO_CODE[xd.dtype], Bi,
+                                                      C.c_void_p(idd.data_ptr()), Bt, T, C.c_void_p(out.data_ptr()),
+                                                      C.c_void_p(_stream_ptr(self.device))))
+                if not host_in:
+                    return out
+                out_h = torch.empty((Bi, Bt), dtype=torch.float32, pin_memory=True)
+                out_h.copy_(out, non_blocking=True)
+                torch.cuda.current_stream(self.device).synchronize()
+                return out_h
             if not x.is_cuda and not ids.is_cuda:
                 out = torch.empty((Bi, Bt), dtype=torch.float32, pin_memory=True)
                 _lib.check(self.lib.jimm_dual_forward_host(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], Bi,

@@ -151,6 +151,31 @@ def test_uint8_frames_through_the_model():
         m(frames[:2])
 
 
+def test_uint8_frames_through_the_dual_towers():
+    """Raw uint8 frames + token ids into CLIP / SigLIP (examples/clip_inference.py:35-47 end to end) and into encode_image: equal to
+    front-end-then-model bit for bit, for host and device inputs."""
+    from jimm_b200.models import CLIP, SigLIP
+    from jimm_b200.preprocess import ImagePreprocessor
+
+    torch.manual_seed(0)
+    frames = torch.randint(0, 256, (6, 40, 56, 3), dtype=torch.uint8)
+    for cls, proc in ((CLIP, ImagePreprocessor.clip(32)), (SigLIP, ImagePreprocessor.siglip(32))):
+        m = cls(image_resolution=32, vision_layers=2, vision_width=128, vision_patch_size=8, context_length=16, vocab_size=100,
+                transformer_width=64, transformer_heads=1, transformer_layers=2, dtype=torch.float16).eval()
+        ids = torch.randint(1, 100, (6, 16), dtype=torch.int32)
+        with pytest.raises(ValueError):
+            m(frames, ids)  # no front-end attached
+        m.set_preprocessor(proc)
+        px = proc(frames.cuda(), dtype=torch.float16)
+        ref = m(px, ids.cuda())
+        assert torch.equal(m(frames.cuda(), ids.cuda()), ref)
+        out_host = m(frames.pin_memory(), ids)
+        assert not out_host.is_cuda and torch.equal(out_host, ref.cpu())
+        emb = m.encode_image(px)
+        assert torch.equal(m.encode_image(frames.cuda()), emb)
+        assert torch.equal(m.encode_image(frames.pin_memory()), emb.cpu())
+
+
 def test_integer_size_is_square_for_vit_and_shortest_edge_for_clip(tmp_path):
     """preprocessor_config.json with a legacy integer `size`: ViTImageProcessor / SiglipImageProcessor read it as a square
     (default_to_square=True), CLIPImageProcessor as the shortest edge."""
