@@ -206,6 +206,8 @@ class NativeModel:
         """encode_image + encode_text of device-resident inputs with the two towers running concurrently (jimm_dual_encode)."""
         Bi, (Bt, T) = x.shape[0], ids.shape
         with torch.cuda.device(self.device):
+            if x.dtype == torch.uint8:  # raw frames: the image front-end first (model.set_preprocessor)
+                x = self.preproc(x, dtype=self._operand_dtype())
             ie = torch.empty((Bi, self.vision_out), dtype=torch.float32, device=self.device)
             te = torch.empty((Bt, self.text_out), dtype=torch.float32, device=self.device)
             _lib.check(self.lib.jimm_dual_encode(self.handle, C.c_void_p(x.data_ptr()), _TORCH_TO_CODE[x.dtype], Bi, C.c_void_p(ids.data_ptr()), Bt, T,

@@ -79,6 +79,11 @@ class DualTower(_NativeOwner, nn.Module):
                     x_d = x.to(n.device, non_blocking=True)
             if x.is_cuda:
                 ie, te = n.dual_encode(x_d, ids_d)  # both towers concurrently (text forked onto the library's side stream)
+            elif x.dtype == torch.uint8:
+                # raw frames are a quarter of the bytes: take the short copy up front and run the two towers concurrently
+                cur.wait_stream(side)
+                x_d.record_stream(cur)
+                ie, te = n.dual_encode(x_d, ids_d)
             else:
                 te = n.text(ids_d)
                 cur.wait_stream(side)

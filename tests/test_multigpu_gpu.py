@@ -63,6 +63,16 @@ def _worker(rank, world, port, kind, q):
     m.set_comm("peer")
     out_h = m(img[lo:hi].pin_memory(), txt[lo:hi].to(torch.int32).pin_memory())
     assert not out_h.is_cuda and torch.equal(out_h, full[lo:hi])
+    # raw uint8 frames (model.set_preprocessor): device frames and pinned host frames equal front-end-then-model bit for bit
+    from jimm_b200.preprocess import ImagePreprocessor
+
+    proc = ImagePreprocessor.clip(64) if kind == "clip" else ImagePreprocessor.siglip(64)
+    m.set_preprocessor(proc)
+    frames = torch.randint(0, 256, (Bg, 64, 64, 3), generator=torch.Generator().manual_seed(5), dtype=torch.uint8)[lo:hi].contiguous()
+    ref_u8 = m(proc(frames.cuda(), dtype=torch.float16), txt[lo:hi].cuda())
+    assert torch.equal(m(frames.cuda(), txt[lo:hi].cuda()), ref_u8)
+    out_u8 = m(frames.pin_memory(), txt[lo:hi].to(torch.int32).pin_memory())
+    assert not out_u8.is_cuda and torch.equal(out_u8, ref_u8.cpu())
     torch.cuda.synchronize()
     dist.barrier()
     q.put((rank, errs))
