@@ -233,11 +233,6 @@ struct jimm_model {
   int epi_mode_16 = 2;  // epilogue mode for 16-bit no-residual outputs (2 = TMA store)
   int epi_mode_res = 2; // epilogue mode for fp32 residual outputs (2 = TMA reduce-add into the residual stream)
   bool l2_alternate = true;  // JIMM_L2_ALTERNATE=0 disables the alternating walk direction
-  // JIMM_L2_PERSIST=<MB>: keep that much of the fp32 residual stream resident in L2 across a tower's kernels (stream access-policy window
-  // over `x`, persisting hits / streaming misses).  x is read by both LayerNorms and read-modified-written by both residual GEMMs of
-  // every block, with ~0.6 GB of qkv / MLP traffic in between that evicts it today.  0 = off (default until measured on every config).
-  int l2_persist_mb = 0;
-  size_t l2_window_max = 0;  // device limit of an access-policy window (0: not queried / unsupported)
   // JIMM_FUSE_LN=1: the out-proj / FC2 GEMMs normalise the rows they complete (gemm.cu, "fused LayerNorm").  Off by default: it removes
   // two launches per block but is SLOWER on every measured shape (14.1 vs 11.5 ms/step, ViT-B/16 B=256) -- the row read-back competes with
   // the GEMM's own TMA traffic for the SM<->L2 ports that already bound it.  Kept for A/B runs and covered by tests.
@@ -579,36 +574,7 @@ static int run_map_head(jimm_model* m, int B, int S, float* out, cudaStream_t s)
 }
 
 // VisionTransformerBase.__call__ (common/vit.py:216-248) + the model's head.  out: fp32 [B, out_dim]
-// Access-policy window over the residual stream for the kernels launched on `s` until l2_window_end (JIMM_L2_PERSIST).
-static void l2_window_begin(jimm_model* m, cudaStream_t s, void* x, size_t bytes) {
-  if (m->l2_persist_mb <= 0 || m->l2_window_max == 0 || bytes < (static_cast<size_t>(16) << 20)) return;
-  cudaStreamAttrValue a;
-  memset(&a, 0, sizeof(a));
-  const size_t win = bytes < m->l2_window_max ? bytes : m->l2_window_max;
-  const double carve = static_cast<double>(static_cast<size_t>(m->l2_persist_mb) << 20);
-  a.accessPolicyWindow.base_ptr = x;
-  a.accessPolicyWindow.num_bytes = win;
-  a.accessPolicyWindow.hitRatio = static_cast<float>(carve >= static_cast<double>(win) ? 1.0 : carve / static_cast<double>(win));
-  a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) (void)cudaGetLastError();
-}
-static void l2_window_end(jimm_model* m, cudaStream_t s) {
-  if (m->l2_persist_mb <= 0 || m->l2_window_max == 0) return;
-  cudaStreamAttrValue a;
-  memset(&a, 0, sizeof(a));
-  a.accessPolicyWindow.num_bytes = 0;  // disables the window for later launches on this stream
-  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) (void)cudaGetLastError();
-}
-
-static int run_vision_body(jimm_model* m, const void* img, int in_dtype, int B, float* out, cudaStream_t s);
 static int run_vision(jimm_model* m, const void* img, int in_dtype, int B, float* out, cudaStream_t s) {
-  l2_window_begin(m, s, m->ws.x, static_cast<size_t>(B) * m->vis.S * m->vis.D * sizeof(float));
-  const int rc = run_vision_body(m, img, in_dtype, B, out, s);
-  l2_window_end(m, s);
-  return rc;
-}
-static int run_vision_body(jimm_model* m, const void* img, int in_dtype, int B, float* out, cudaStream_t s) {
   VisionTower& v = m->vis;
   Workspace& ws = m->ws;
   const int D = v.D, S = v.S, n = v.n;
@@ -871,29 +837,6 @@ int jimm_model_create(const jimm_config_t* cfg, int device, jimm_model_t** out) 
   if ((env = getenv("JIMM_GRAPH_MAX_BATCH"))) m->graph_max_batch = atoi(env) > 0 ? atoi(env) : 0;
   if ((env = getenv("JIMM_DUAL_STREAMS"))) m->dual_streams = atoi(env) != 0;
   if ((env = getenv("JIMM_FUSE_LN"))) m->fuse_ln = atoi(env) != 0;
-  if ((env = getenv("JIMM_L2_PERSIST"))) m->l2_persist_mb = atoi(env) > 0 ? atoi(env) : 0;
-  if (m->l2_persist_mb > 0) {
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
-      size_t want = static_cast<size_t>(m->l2_persist_mb) << 20;
-      if (want > static_cast<size_t>(prop.persistingL2CacheMaxSize)) want = static_cast<size_t>(prop.persistingL2CacheMaxSize);
-      int cur_dev = device;
-      (void)cudaGetDevice(&cur_dev);
-      (void)cudaSetDevice(device);  // the limit is a property of the current device
-      const cudaError_t lim = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-      (void)cudaSetDevice(cur_dev);
-      if (lim == cudaSuccess) {
-        m->l2_persist_mb = static_cast<int>(want >> 20);
-        m->l2_window_max = static_cast<size_t>(prop.accessPolicyMaxWindowSize);
-      } else {
-        (void)cudaGetLastError();
-        m->l2_persist_mb = 0;
-      }
-    } else {
-      (void)cudaGetLastError();
-      m->l2_persist_mb = 0;
-    }
-  }
   if ((env = getenv("JIMM_EPI_MODE_16"))) m->epi_mode_16 = atoi(env);
   if ((env = getenv("JIMM_EPI_MODE_RES"))) m->epi_mode_res = atoi(env);
   *out = m;
