@@ -293,6 +293,20 @@ def test_embed_l2_logits(lib):
     assert rel_err(out, ref + 1.7) < 1e-6
 
 
+@pytest.mark.parametrize("Bi,Bt,E", [(70, 133, 100), (5, 300, 50), (64, 64, 7), (129, 65, 1024)])
+def test_logits_tile_shapes(lib, Bi, Bt, E):
+    """logits_tile.cuh: E % 16 != 0 on the 128-bit path (100), the scalar fallback for E % 4 != 0 (50, 7), ragged row / column tiles and a
+    strided (sliced) text operand."""
+    a = torch.nn.functional.normalize(torch.randn(Bi, E, device=DEV), dim=-1)
+    b = torch.nn.functional.normalize(torch.randn(Bt, E, device=DEV), dim=-1)
+    sc, bs = torch.tensor([1.1], device=DEV), torch.tensor([0.4], device=DEV)
+    out = torch.full((Bi, Bt + 3), 7.0, device=DEV)  # row stride larger than Bt: the columns beyond Bt must stay untouched
+    check(lib, lib.jimm_k_logits(ptr(a), ptr(b), ptr(sc), ptr(bs), ptr(out), Bi, Bt, E, Bt + 3, stream()))
+    ref = math.exp(1.1) * (a.double() @ b.double().T) + 0.4
+    assert rel_err(out[:, :Bt], ref) < 1e-6
+    assert torch.all(out[:, Bt:] == 7.0)
+
+
 def test_bad_arguments_return_errors(lib):
     A = torch.zeros(8, 8, device=DEV).half()
     out = torch.zeros(8, 6, device=DEV)
